@@ -1,0 +1,120 @@
+/*
+ * srm.h — C ABI of libsrm.so: the B200-native (sm_100a) discrete-CVT Lloyd engine that
+ * replaces Surface-Remesher's GPU hot path.  Plain pointers and sizes only.
+ *
+ * Reference interfaces replaced (paths relative to the reference's source/):
+ *   srm_gcvt        <- void gCVT(short*,float*,bool*,int,int,int)          gcvt.h:29, gcvt.cu:1087
+ *   srm_discretize  <- void discretization_d(double*,double*,int,int*,int,
+ *                                            float*,double,int)            discretization.h:66, discretization.cu:87
+ *   srm_seed        <- putConstrains + randomPoints                        gcvt.h:76-122
+ *   srm_generate_mask <- generateMask                                      gcvt.h:143-159
+ * The C++ shims with the reference's exact (mangled) signatures live in
+ * surface-remesher_b200/csrc/srm_dropin.cpp (libsrm_dropin.so); INTEGRATION.md shows
+ * how an unmodified main.cpp links against them.
+ *
+ * Conventions: index = y*n + x (TOID, gcvt.cu:38); a label / site is a little-endian
+ * short2 (x,y) == one int32 `(uint16)x | (uint16)y << 16`; empty = MARKER = -32768 in
+ * both halves (gcvt.cu:37).  Every function returns SRM_OK or an error code; the text
+ * of the last error on the calling thread is srm_last_error().  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with SRM_ERR_CUDA.
+ */
+#ifndef SRM_H
+#define SRM_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRM_MARKER (-32768)
+
+enum {
+    SRM_OK = 0,
+    SRM_ERR_ARG = 1,      /* bad size / null pointer / unsupported n */
+    SRM_ERR_CUDA = 2,     /* CUDA runtime error (message in srm_last_error) */
+    SRM_ERR_STATE = 3,    /* call order (e.g. iterate before density/sites are set) */
+    SRM_ERR_SEED = 4      /* seeding could not place the requested number of sites */
+};
+
+typedef struct srm_ctx srm_ctx;
+
+typedef struct srm_stats {
+    int iterations;      /* Lloyd iterations executed (gcvtIterations, gcvt.cu:1086) */
+    int num_sites;       /* sites alive at the end (sites merge, gcvt.cu:779-780) */
+    int stopped;         /* 1 if the reference stopping rule fired (gcvt.cu:1136) */
+    float omega;         /* over-relaxation factor at exit (gcvt.cu:1131) */
+    float energy;        /* last energy computed (gcvt.cu:1117), as float like the reference */
+    float ms_device;     /* device time of the loop + final labelling (CUDA events) */
+} srm_stats;
+
+const char *srm_last_error(void);
+int srm_version(void);
+
+/* ------------------------------------------------------------ one-shot drop-ins (host buffers) */
+
+/* gCVT (gcvt.cu:1087-1156): voronoi in = seed map, out = label map of the final sites.
+ * depth > 1 is clamped like gcvt.cu:1091 and then run as a single level.
+ * stats may be NULL. */
+int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
+             srm_stats *stats);
+
+/* discretization_d (discretization.cu:87-120): first triangle (index order) containing the
+ * sample (x*scale, y*scale) gives the barycentric interpolation of the vertex weights; 0 if none. */
+int srm_discretize(const double *points, const double *weight, int num_point, const int *triangle, int num_tri,
+                   float *density, double scale, int n);
+
+/* putConstrains + randomPoints (gcvt.h:76-122), LP64 semantics of the never-seeded RNG.
+ * *rng_state in/out (reference: 0; may be NULL).  mask may be NULL. */
+int srm_seed(short *voronoi, const float *density, const unsigned char *mask, int num, int n,
+             unsigned long long *rng_state);
+
+/* generateMask (gcvt.h:143-159): mask[int((p-l)/scale)] = 1 for every constraint point (x,y pairs). */
+int srm_generate_mask(unsigned char *mask, const double *points_xy, int num_points, int n, double scale,
+                      double left, double lower);
+
+/* ------------------------------------------------------------ handle API (device-resident state) */
+
+/* A context owns rows [row0,row1) of an n x n grid on `device` (row0 = 0, row1 = n for a whole
+ * grid; row bands for multi-GPU sharding).  n: multiple of 256, 256..32768;
+ * row0,row1: multiples of 64.  Site list, site bitmap, density and mask are replicated per band. */
+int srm_create(srm_ctx **out, int n, int row0, int row1, int device);
+int srm_destroy(srm_ctx *ctx);
+/* Run all work of this context on an existing CUDA stream (cudaStream_t passed as void*). */
+int srm_set_stream(srm_ctx *ctx, void *cuda_stream);
+int srm_synchronize(srm_ctx *ctx);
+
+/* Inputs: full-grid arrays (n*n).  on_device != 0 means the pointer is device memory on ctx's device. */
+int srm_set_density(srm_ctx *ctx, const float *density, int on_device);
+int srm_set_mask(srm_ctx *ctx, const unsigned char *mask, int on_device); /* NULL = no constraints */
+/* Sites from a dense seed map (short2 per pixel) or from a packed list. */
+int srm_set_site_map(srm_ctx *ctx, const short *site_map, int on_device);
+int srm_set_sites(srm_ctx *ctx, const int *packed_xy, int num, int on_device);
+int srm_get_sites(srm_ctx *ctx, int *packed_xy_host, int capacity, int *num_out);
+int srm_set_omega(srm_ctx *ctx, float omega);
+
+/* Steps of one Lloyd iteration (gcvt.cu:1112-1123), all asynchronous on the context's stream. */
+int srm_label(srm_ctx *ctx);                       /* pba2DCompute: exact labels of the current sites (run-length form) */
+int srm_accumulate(srm_ctx *ctx, int want_energy); /* pbaCVDComputeCentroid (+pbaCVDCalcEnergy): per-site sums over this band */
+int srm_update(srm_ctx *ctx);                      /* pbaCVDUpdateSites + the control block of gcvt.cu:1123-1140 */
+/* Device accumulators for an external all-reduce between srm_accumulate and srm_update:
+ * 4*capacity+4 doubles: (W, X, Y, 0) per site, then (energy_sum,0,0,0). */
+int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
+
+/* iters x (label, accumulate, update) with the reference's energy/omega schedule; stop_rule != 0
+ * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */
+int srm_iterate(srm_ctx *ctx, int iters, int stop_rule);
+/* Whole gCVT on resident inputs: loop + final labelling. */
+int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);
+int srm_get_state(srm_ctx *ctx, srm_stats *stats);
+
+/* Dense labels of this band (rows row0..row1): expands the run-length labels of the last srm_label.
+ * out: (row1-row0)*n short2. */
+int srm_get_labels(srm_ctx *ctx, short *out, int on_device);
+/* Alternative labelling (north_star kernel family, NOT the reference's algorithm): jump flooding with
+ * the given step schedule on the current sites, whole-grid contexts only; result as dense labels. */
+int srm_label_jfa(srm_ctx *ctx, const int *steps, int nsteps, short *out, int on_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRM_H */

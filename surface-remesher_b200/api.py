@@ -1,0 +1,284 @@
+"""ctypes binding of libsrm.so and the reference-named host functions.
+
+Names, argument order and meaning follow the reference (source/gcvt.h:29,76-159,
+source/discretization.h:66-67); arrays are numpy, modified in place where the reference
+modifies its buffers in place.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MARKER = -32768
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+
+
+class SrmError(RuntimeError):
+    pass
+
+
+class Stats(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("num_sites", C.c_int), ("stopped", C.c_int), ("omega", C.c_float),
+                ("energy", C.c_float), ("ms_device", C.c_float)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsrm.so")
+
+
+def lib():
+    """Load libsrm.so (built in-tree by __graft_entry__.build() / csrc/Makefile).  Fails loudly."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SrmError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    p, i, d = C.c_void_p, C.c_int, C.c_double
+    L.srm_last_error.restype = C.c_char_p
+    L.srm_version.restype = i
+    L.srm_gcvt.argtypes = [p, p, p, i, i, i, p]
+    L.srm_discretize.argtypes = [p, p, i, p, i, p, d, i]
+    L.srm_seed.argtypes = [p, p, p, i, i, p]
+    L.srm_generate_mask.argtypes = [p, p, i, i, d, d, d]
+    L.srm_create.argtypes = [C.POINTER(p), i, i, i, i]
+    L.srm_destroy.argtypes = [p]
+    L.srm_set_stream.argtypes = [p, p]
+    L.srm_synchronize.argtypes = [p]
+    L.srm_set_density.argtypes = [p, p, i]
+    L.srm_set_mask.argtypes = [p, p, i]
+    L.srm_set_site_map.argtypes = [p, p, i]
+    L.srm_set_sites.argtypes = [p, p, i, i]
+    L.srm_get_sites.argtypes = [p, p, i, C.POINTER(i)]
+    L.srm_set_omega.argtypes = [p, C.c_float]
+    L.srm_label.argtypes = [p]
+    L.srm_accumulate.argtypes = [p, i]
+    L.srm_update.argtypes = [p]
+    L.srm_acc_buffer.argtypes = [p, C.POINTER(p), C.POINTER(C.c_size_t)]
+    L.srm_iterate.argtypes = [p, i, i]
+    L.srm_run.argtypes = [p, i, i, p]
+    L.srm_get_state.argtypes = [p, p]
+    L.srm_get_labels.argtypes = [p, p, i]
+    L.srm_label_jfa.argtypes = [p, p, i, p, i]
+    for name in ("srm_gcvt", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
+                 "srm_set_stream", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
+                 "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_label", "srm_accumulate", "srm_update",
+                 "srm_acc_buffer", "srm_iterate", "srm_run", "srm_get_state", "srm_get_labels", "srm_label_jfa"):
+        getattr(L, name).restype = i
+    _lib = L
+    return L
+
+
+def _ck(rc):
+    if rc != 0:
+        raise SrmError(f"libsrm error {rc}: {lib().srm_last_error().decode()}")
+
+
+def _np(a, dtype, shape=None):
+    if not isinstance(a, np.ndarray) or a.dtype != np.dtype(dtype) or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"expected a C-contiguous numpy array of {np.dtype(dtype)}")
+    if shape is not None and a.size != int(np.prod(shape)):
+        raise ValueError(f"expected {int(np.prod(shape))} elements, got {a.size}")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _mask_ptr(mask, n):
+    if mask is None:
+        return None, None
+    m = mask if (isinstance(mask, np.ndarray) and mask.dtype in (np.uint8, np.bool_) and mask.flags["C_CONTIGUOUS"]) \
+        else np.ascontiguousarray(mask, dtype=np.uint8)
+    if m.size != n * n:
+        raise ValueError("mask must have n*n elements")
+    return m, m.ctypes.data_as(C.c_void_p)
+
+
+# ---------------------------------------------------------------- reference-named functions
+
+def gCVT(Voronoi, density_d, mask, size, depth, maxIter):
+    """gcvt.h:29 / gcvt.cu:1087.  Voronoi: int16[size*size*2] in = seed map, out = final label map."""
+    st = Stats()
+    keep, mp = _mask_ptr(mask, size)
+    _ck(lib().srm_gcvt(_np(Voronoi, np.int16, (size, size, 2)), _np(density_d, np.float32, (size, size)), mp,
+                       int(size), int(depth), int(maxIter), C.byref(st)))
+    return st.as_dict()
+
+
+def discretization_d(points, weight, num_point, triangle, num_tri, density, scale, n):
+    """discretization.h:66 / discretization.cu:87.  density: float32[n*n], written."""
+    _ck(lib().srm_discretize(_np(points, np.float64, (num_point, 2)), _np(weight, np.float64, (num_point,)),
+                             int(num_point), _np(triangle, np.int32, (num_tri, 3)), int(num_tri),
+                             _np(density, np.float32, (n, n)), float(scale), int(n)))
+
+
+def putConstrains(Voronoi, mask, n):
+    """gcvt.h:106-122."""
+    keep, mp = _mask_ptr(mask, n)
+    d = np.ones((1,), np.float32)  # unused with num=0
+    dens = np.ones((n, n), np.float32)
+    _ck(lib().srm_seed(_np(Voronoi, np.int16, (n, n, 2)), _np(dens, np.float32), mp, 0, int(n), None))
+    del d
+
+
+def randomPoints(Voronoi, density, num, size, state=0):
+    """gcvt.h:76-104 on an already constrained map; returns the RNG state (reference: starts at 0)."""
+    n = size
+    st = C.c_ulonglong(state)
+    # srm_seed = putConstrains + randomPoints; keep the sites already present by passing them as the mask
+    v = Voronoi.reshape(n, n, 2)
+    present = np.ascontiguousarray((v[..., 0] != MARKER).astype(np.uint8))
+    _ck(lib().srm_seed(_np(Voronoi, np.int16, (n, n, 2)), _np(density, np.float32, (n, n)),
+                       present.ctypes.data_as(C.c_void_p), int(num), int(n), C.byref(st)))
+    return st.value
+
+
+def centroidalVoronoi(Voronoi, density, constrainMask, vertices, imageSize, depth, maxIter):
+    """gcvt.h:124-139: putConstrains, randomPoints, gCVT."""
+    keep, mp = _mask_ptr(constrainMask, imageSize)
+    _ck(lib().srm_seed(_np(Voronoi, np.int16, (imageSize, imageSize, 2)), _np(density, np.float32), mp,
+                       int(vertices), int(imageSize), None))
+    return gCVT(Voronoi, density, constrainMask, imageSize, depth, maxIter)
+
+
+def generateMask(points_xy, mask, imageSize, scale, l, b):
+    """gcvt.h:143-159 with the constraint points given as an (M,2) float64 array."""
+    pts = np.ascontiguousarray(points_xy, np.float64)
+    _ck(lib().srm_generate_mask(_np(mask, np.uint8, (imageSize, imageSize)), _np(pts, np.float64), len(pts),
+                                int(imageSize), float(scale), float(l), float(b)))
+
+
+# ---------------------------------------------------------------- handle API
+
+def row_bands(n, world):
+    """Row-band partition of an n-row grid over `world` ranks: equal bands, multiples of 64 rows."""
+    if n % (64 * world):
+        raise ValueError(f"n={n} is not divisible into {world} bands of a multiple of 64 rows")
+    h = n // world
+    return [(r * h, (r + 1) * h) for r in range(world)]
+
+
+def _ptr(a):
+    """Device or host pointer of a numpy array / torch tensor -> (void*, on_device)."""
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise TypeError("array must be C-contiguous")
+        return a.ctypes.data_as(C.c_void_p), 0
+    if hasattr(a, "data_ptr"):  # torch tensor
+        if not a.is_contiguous():
+            raise TypeError("tensor must be contiguous")
+        return C.c_void_p(a.data_ptr()), 1 if a.is_cuda else 0
+    raise TypeError(type(a))
+
+
+class Context:
+    """Device-resident Lloyd state for rows [row0,row1) of an n x n grid (include/srm.h handle API)."""
+
+    def __init__(self, n, row0=0, row1=None, device=0):
+        self.n, self.row0, self.row1 = int(n), int(row0), int(n if row1 is None else row1)
+        self._h = C.c_void_p()
+        _ck(lib().srm_create(C.byref(self._h), self.n, self.row0, self.row1, int(device)))
+
+    def close(self):
+        if self._h:
+            lib().srm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr):
+        _ck(lib().srm_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        _ck(lib().srm_synchronize(self._h))
+
+    def set_density(self, density):
+        p, dev = _ptr(density)
+        _ck(lib().srm_set_density(self._h, p, dev))
+
+    def set_mask(self, mask):
+        if mask is None:
+            _ck(lib().srm_set_mask(self._h, None, 0))
+            return
+        if isinstance(mask, np.ndarray) and mask.dtype == np.bool_:
+            mask = mask.view(np.uint8)
+        p, dev = _ptr(mask)
+        _ck(lib().srm_set_mask(self._h, p, dev))
+
+    def set_site_map(self, site_map):
+        p, dev = _ptr(site_map)
+        _ck(lib().srm_set_site_map(self._h, p, dev))
+
+    def set_sites(self, packed_xy):
+        p, dev = _ptr(packed_xy)
+        _ck(lib().srm_set_sites(self._h, p, int(packed_xy.shape[0]), dev))
+
+    def get_sites(self):
+        k = C.c_int()
+        _ck(lib().srm_get_sites(self._h, None, 0, C.byref(k)))
+        out = np.empty(k.value, np.int32)
+        _ck(lib().srm_get_sites(self._h, out.ctypes.data_as(C.c_void_p), k.value, C.byref(k)))
+        return out[: k.value]
+
+    def set_omega(self, omega):
+        _ck(lib().srm_set_omega(self._h, float(omega)))
+
+    def label(self):
+        _ck(lib().srm_label(self._h))
+
+    def accumulate(self, want_energy):
+        _ck(lib().srm_accumulate(self._h, int(bool(want_energy))))
+
+    def update(self):
+        _ck(lib().srm_update(self._h))
+
+    def acc_buffer(self):
+        """(device pointer, number of doubles) of the per-site accumulators, for an external all-reduce."""
+        p, cnt = C.c_void_p(), C.c_size_t()
+        _ck(lib().srm_acc_buffer(self._h, C.byref(p), C.byref(cnt)))
+        return p.value, cnt.value
+
+    def iterate(self, iters, stop_rule=False):
+        _ck(lib().srm_iterate(self._h, int(iters), int(bool(stop_rule))))
+
+    def run(self, max_iter, stop_rule=True):
+        st = Stats()
+        _ck(lib().srm_run(self._h, int(max_iter), int(bool(stop_rule)), C.byref(st)))
+        return st.as_dict()
+
+    def state(self):
+        st = Stats()
+        _ck(lib().srm_get_state(self._h, C.byref(st)))
+        return st.as_dict()
+
+    def get_labels(self, out=None):
+        rows = self.row1 - self.row0
+        if out is None:
+            out = np.empty((rows, self.n, 2), np.int16)
+        p, dev = _ptr(out)
+        _ck(lib().srm_get_labels(self._h, p, dev))
+        return out
+
+    def label_jfa(self, steps, out=None):
+        st = np.ascontiguousarray(steps, np.int32)
+        if out is None:
+            out = np.empty((self.n, self.n, 2), np.int16)
+        p, dev = _ptr(out)
+        _ck(lib().srm_label_jfa(self._h, st.ctypes.data_as(C.c_void_p), len(st), p, dev))
+        return out
+
+
+def unpack_sites(packed):
+    """int32 packed sites -> (K,2) int16 (x,y)."""
+    p = np.asarray(packed, np.int32)
+    return np.stack([(p & 0xFFFF).astype(np.uint16).view(np.int16), (p >> 16).astype(np.int16)], 1)

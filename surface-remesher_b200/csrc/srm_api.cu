@@ -1,0 +1,554 @@
+// srm_api.cu — context management and the C ABI of libsrm.so (include/srm.h).
+//
+// Host side of the hot path: what gcvtInitialization / pba2DInitializeInput / gCVT /
+// pbaCVDDeinitialization (gcvt.cu:840-914, 1087-1156) and discretization_d
+// (discretization.cu:87-120) do around the kernels, re-designed so that all loop state stays on
+// the device (no host sync per iteration; the reference blocks on a 4-byte D2H every 10th
+// iteration, gcvt.cu:1080) and a context can own a row band of the grid for multi-GPU sharding.
+#include "../../include/srm.h"
+#include "srm_common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(SRM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+extern "C" const char *srm_last_error(void) { return g_err; }
+extern "C" int srm_version(void) { return 100; }
+
+struct srm_ctx {
+    SrmGrid g{};
+    int device = 0;
+    size_t N = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // inputs (full grid) and per-band derived data
+    float *density = nullptr;
+    unsigned char *mask = nullptr;
+    bool has_mask = false, has_density = false, has_sites = false, labelled = false;
+    double2 *P2 = nullptr;
+    double *PXX = nullptr;
+    // sites
+    int *sites[2] = {nullptr, nullptr};
+    int cur = 0, Kcap = 0;
+    double *acc = nullptr;
+    int *newpos = nullptr, *blockcnt = nullptr, *blockoff = nullptr;
+    size_t blockcap = 0;
+    // labelling state
+    uint32_t *bits = nullptr;
+    short *up = nullptr, *dn = nullptr, *cy = nullptr;
+    int2 *rle = nullptr;
+    int *rle_cnt = nullptr, *idmap = nullptr, *claim = nullptr, *labels = nullptr, *scratch_map = nullptr;
+    SrmCtl *ctl = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
+    bool stopped = false;
+};
+
+static int valid_n(int n) { return n >= 256 && n <= 32768 && (n % 256) == 0; }
+
+static int alloc_sites(srm_ctx *c, int K) {
+    for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
+    if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
+    if (c->newpos) { cudaFree(c->newpos); c->newpos = nullptr; }
+    c->Kcap = K;
+    size_t k1 = (size_t)(K > 0 ? K : 1);
+    CK(cudaMalloc(&c->sites[0], k1 * sizeof(int)));
+    CK(cudaMalloc(&c->sites[1], k1 * sizeof(int)));
+    CK(cudaMalloc(&c->newpos, k1 * sizeof(int)));
+    CK(cudaMalloc(&c->acc, (4 * (size_t)K + 4) * sizeof(double)));
+    CK(cudaMemsetAsync(c->acc, 0, (4 * (size_t)K + 4) * sizeof(double), c->stream));
+    c->cur = 0;
+    return SRM_OK;
+}
+
+static int reset_ctl(srm_ctx *c, int K) {
+    SrmCtl h;
+    memset(&h, 0, sizeof(h));
+    h.K = K; h.Knext = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
+    CK(cudaMemcpyAsync(c->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // h is a stack object
+    c->it_host = 0;
+    c->stopped = false;
+    c->labelled = false;
+    return SRM_OK;
+}
+
+extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) {
+    if (!out) return fail(SRM_ERR_ARG, "srm_create: null out");
+    *out = nullptr;
+    if (!valid_n(n)) return fail(SRM_ERR_ARG, "srm_create: n=%d unsupported (multiple of 256 in [256,32768])", n);
+    if (row0 < 0 || row1 > n || row0 >= row1 || (row0 % 64) || (row1 % 64))
+        return fail(SRM_ERR_ARG, "srm_create: rows [%d,%d) must be multiples of 64 within [0,%d]", row0, row1, n);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRM_ERR_CUDA, "srm_create: no CUDA device (libsrm has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(SRM_ERR_ARG, "srm_create: device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    srm_ctx *c = new srm_ctx();
+    c->g.n = n; c->g.row0 = row0; c->g.row1 = row1;
+    c->device = device;
+    c->N = (size_t)n * n;
+    const size_t NB = (size_t)c->g.nrows() * n, NW = (size_t)(n >> 5) * n;
+#define CKD(call)                                                                                        \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            srm_destroy(c);                                                                              \
+            return fail(SRM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                       \
+        }                                                                                                \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+    CKD(cudaEventCreate(&c->ev0));
+    CKD(cudaEventCreate(&c->ev1));
+    CKD(cudaMalloc(&c->density, c->N * sizeof(float)));
+    CKD(cudaMalloc(&c->mask, c->N));
+    CKD(cudaMalloc(&c->P2, NB * sizeof(double2)));
+    CKD(cudaMalloc(&c->PXX, NB * sizeof(double)));
+    CKD(cudaMalloc(&c->bits, NW * sizeof(uint32_t)));
+    CKD(cudaMalloc(&c->up, NW * sizeof(short)));
+    CKD(cudaMalloc(&c->dn, NW * sizeof(short)));
+    CKD(cudaMalloc(&c->cy, NB * sizeof(short)));
+    CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
+    CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
+    CKD(cudaMalloc(&c->idmap, c->N * sizeof(int)));
+    CKD(cudaMalloc(&c->claim, c->N * sizeof(int)));
+    CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
+    c->blockcap = c->N / 256 + 2;  // covers both the seed-map compaction (N/1024 tiles) and K <= N sites
+    CKD(cudaMalloc(&c->blockcnt, c->blockcap * sizeof(int)));
+    CKD(cudaMalloc(&c->blockoff, c->blockcap * sizeof(int)));
+    CKD(cudaMemsetAsync(c->ctl, 0, sizeof(SrmCtl), c->stream));
+    CKD(srm_label_setup(n));
+    srm_launch_fill_int(c->stream, c->claim, c->N, INT_MAX);
+    CKD(cudaGetLastError());
+    CKD(cudaStreamSynchronize(c->stream));
+#undef CKD
+    *out = c;
+    return SRM_OK;
+}
+
+extern "C" int srm_destroy(srm_ctx *c) {
+    if (!c) return SRM_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
+                    c->blockoff, c->bits, c->up, c->dn, c->cy, c->rle, c->rle_cnt, c->idmap, c->claim, c->labels,
+                    c->scratch_map, c->ctl};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SRM_OK;
+}
+
+extern "C" int srm_set_stream(srm_ctx *c, void *cuda_stream) {
+    if (!c) return fail(SRM_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    c->stream = (cudaStream_t)cuda_stream;
+    c->own_stream = false;
+    return SRM_OK;
+}
+
+extern "C" int srm_synchronize(srm_ctx *c) {
+    if (!c) return fail(SRM_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return SRM_OK;
+}
+
+extern "C" int srm_set_density(srm_ctx *c, const float *density, int on_device) {
+    if (!c || !density) return fail(SRM_ERR_ARG, "srm_set_density: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->density, density, c->N * sizeof(float),
+                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    // pbaCVDComputeWeightedPrefix (gcvt.cu:995-1006), fp64, rows of this band only
+    srm_launch_prefix(c->stream, c->density + (size_t)c->g.row0 * c->g.n, c->g, c->P2, c->PXX);
+    CK(cudaGetLastError());
+    if (!on_device) CK(cudaStreamSynchronize(c->stream));  // pageable source must stay valid
+    c->has_density = true;
+    return SRM_OK;
+}
+
+extern "C" int srm_set_mask(srm_ctx *c, const unsigned char *mask, int on_device) {
+    if (!c) return fail(SRM_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    if (!mask) { c->has_mask = false; return SRM_OK; }
+    CK(cudaMemcpyAsync(c->mask, mask, c->N, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (!on_device) CK(cudaStreamSynchronize(c->stream));
+    c->has_mask = true;
+    return SRM_OK;
+}
+
+extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device) {
+    if (!c || !site_map) return fail(SRM_ERR_ARG, "srm_set_site_map: null argument");
+    CK(cudaSetDevice(c->device));
+    const int *dmap = (const int *)site_map;
+    if (!on_device) {
+        if (!c->scratch_map) CK(cudaMalloc(&c->scratch_map, c->N * sizeof(int)));
+        CK(cudaMemcpyAsync(c->scratch_map, site_map, c->N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        dmap = c->scratch_map;
+    }
+    int rc;
+    srm_launch_sites_from_map(c->stream, dmap, c->N, nullptr, c->blockcnt, c->blockoff, c->ctl, 1);
+    CK(cudaGetLastError());
+    SrmCtl h;
+    CK(cudaMemcpyAsync(&h, c->ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const int K = h.Knext;
+    rc = alloc_sites(c, K);
+    if (rc) return rc;
+    srm_launch_sites_from_map(c->stream, dmap, c->N, c->sites[0], c->blockcnt, c->blockoff, c->ctl, 0);
+    CK(cudaGetLastError());
+    rc = reset_ctl(c, K);
+    if (rc) return rc;
+    c->has_sites = true;
+    return SRM_OK;
+}
+
+extern "C" int srm_set_sites(srm_ctx *c, const int *packed_xy, int num, int on_device) {
+    if (!c || (!packed_xy && num > 0) || num < 0) return fail(SRM_ERR_ARG, "srm_set_sites: bad argument");
+    CK(cudaSetDevice(c->device));
+    int rc = alloc_sites(c, num);
+    if (rc) return rc;
+    if (num > 0)
+        CK(cudaMemcpyAsync(c->sites[0], packed_xy, (size_t)num * sizeof(int),
+                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    rc = reset_ctl(c, num);
+    if (rc) return rc;
+    c->has_sites = true;
+    return SRM_OK;
+}
+
+static int fetch_ctl(srm_ctx *c, SrmCtl *h) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(h, c->ctl, sizeof(*h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->it_host = h->it;  // iterations enqueued after a device-side stop were no-ops
+    c->stopped = h->stop != 0;
+    return SRM_OK;
+}
+
+// The live site list is in sites[it & 1]: every executed iteration flips the buffer.
+static int current_buffer(srm_ctx *c) { return c->it_host & 1; }
+
+extern "C" int srm_get_sites(srm_ctx *c, int *packed_xy_host, int capacity, int *num_out) {
+    if (!c || !num_out) return fail(SRM_ERR_ARG, "srm_get_sites: null argument");
+    if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_get_sites: no sites set");
+    SrmCtl h;
+    int rc = fetch_ctl(c, &h);
+    if (rc) return rc;
+    *num_out = h.K;
+    if (packed_xy_host) {
+        int k = std::min(capacity, h.K);
+        if (k > 0) CK(cudaMemcpy(packed_xy_host, c->sites[current_buffer(c)], (size_t)k * sizeof(int),
+                                 cudaMemcpyDeviceToHost));
+    }
+    return SRM_OK;
+}
+
+extern "C" int srm_set_omega(srm_ctx *c, float omega) {
+    if (!c) return fail(SRM_ERR_ARG, "null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&c->ctl->omega, &omega, sizeof(float), cudaMemcpyHostToDevice));
+    return SRM_OK;
+}
+
+// it_host counts enqueued iterations; the buffer parity on the device is (executed iterations) & 1.
+// Inside the loop both agree until a stop; after a stop every kernel is a no-op, so using the
+// host parity for the (skipped) launches is harmless.  For calls outside the loop (final labelling)
+// the parity is read back from the device.
+static int label_with(srm_ctx *c, int buf, int respect_stop) {
+    srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop);
+    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop);
+    srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, c->ctl, respect_stop);
+    CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, c->ctl, respect_stop));
+    return SRM_OK;
+}
+
+static int require_ready(srm_ctx *c, const char *who, bool need_density) {
+    if (!c) return fail(SRM_ERR_ARG, "%s: null ctx", who);
+    if (!c->has_sites) return fail(SRM_ERR_STATE, "%s: sites not set", who);
+    if (need_density && !c->has_density) return fail(SRM_ERR_STATE, "%s: density not set", who);
+    return SRM_OK;
+}
+
+extern "C" int srm_label(srm_ctx *c) {
+    int rc = require_ready(c, "srm_label", false);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    rc = label_with(c, current_buffer(c), 0);
+    if (rc) return rc;
+    c->labelled = true;
+    return SRM_OK;
+}
+
+extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
+    int rc = require_ready(c, "srm_accumulate", true);
+    if (rc) return rc;
+    if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
+    CK(cudaSetDevice(c->device));
+    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl, want_energy, 0);
+    CK(cudaGetLastError());
+    return SRM_OK;
+}
+
+extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles) {
+    if (!c || !device_ptr || !num_doubles) return fail(SRM_ERR_ARG, "srm_acc_buffer: null argument");
+    if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_acc_buffer: sites not set");
+    *device_ptr = c->acc;
+    *num_doubles = 4 * (size_t)c->Kcap + 4;
+    return SRM_OK;
+}
+
+// Stepwise update (manual loop: label / accumulate / [all-reduce] / update).  No host sync: the
+// iteration count is mirrored on the host; the stopping rule is not applied in stepwise mode (the
+// caller reads srm_get_state when it wants to stop), omega still follows gcvt.cu:1131.
+extern "C" int srm_update(srm_ctx *c) {
+    int rc = require_ready(c, "srm_update", true);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const int buf = current_buffer(c);
+    srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
+                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt, c->blockoff, (c->it_host % 10) == 0,
+                      0, 0);
+    CK(cudaGetLastError());
+    c->labelled = false;
+    c->it_host += 1;
+    return SRM_OK;
+}
+
+extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
+    int rc = require_ready(c, "srm_iterate", true);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    if (c->stopped) return SRM_OK;
+    int it = c->it_host;
+    for (int i = 0; i < iters; ++i, ++it) {
+        const int buf = it & 1, want_energy = (it % 10) == 0;
+        rc = label_with(c, buf, 1);
+        if (rc) return rc;
+        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl,
+                       want_energy, 1);
+        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
+                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt,
+                          c->blockoff, want_energy, stop_rule, 1);
+    }
+    CK(cudaGetLastError());
+    c->it_host = it;
+    c->labelled = false;
+    if (stop_rule) {  // the device may have stopped early: resynchronise the host mirror
+        SrmCtl h;
+        rc = fetch_ctl(c, &h);
+        if (rc) return rc;
+    }
+    return SRM_OK;
+}
+
+static void fill_stats(const SrmCtl &h, srm_stats *s, float ms) {
+    if (!s) return;
+    s->iterations = h.it; s->num_sites = h.K; s->stopped = h.stop; s->omega = h.omega; s->energy = h.E; s->ms_device = ms;
+}
+
+extern "C" int srm_get_state(srm_ctx *c, srm_stats *stats) {
+    if (!c || !stats) return fail(SRM_ERR_ARG, "srm_get_state: null argument");
+    SrmCtl h;
+    int rc = fetch_ctl(c, &h);
+    if (rc) return rc;
+    fill_stats(h, stats, 0.0f);
+    return SRM_OK;
+}
+
+extern "C" int srm_run(srm_ctx *c, int max_iter, int stop_rule, srm_stats *stats) {
+    int rc = require_ready(c, "srm_run", true);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    // the loop always runs at least one iteration (do/while, gcvt.cu:1112-1142)
+    rc = srm_iterate(c, std::max(1, max_iter), stop_rule);
+    if (rc) return rc;
+    rc = srm_label(c);  // final pba2DCompute (gcvt.cu:1149)
+    if (rc) return rc;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    SrmCtl h;
+    rc = fetch_ctl(c, &h);
+    if (rc) return rc;
+    fill_stats(h, stats, ms);
+    return SRM_OK;
+}
+
+extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
+    if (!c || !out) return fail(SRM_ERR_ARG, "srm_get_labels: null argument");
+    if (!c->labelled) return fail(SRM_ERR_STATE, "srm_get_labels: call srm_label first");
+    CK(cudaSetDevice(c->device));
+    const size_t NB = (size_t)c->g.nrows() * c->g.n;
+    int *dst = on_device ? (int *)out : nullptr;
+    if (!on_device) {
+        if (!c->labels) CK(cudaMalloc(&c->labels, NB * sizeof(int)));
+        dst = c->labels;
+    }
+    CK(srm_launch_expand(c->stream, c->rle, c->rle_cnt, c->g, dst));
+    if (!on_device) CK(cudaMemcpyAsync(out, dst, NB * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SRM_OK;
+}
+
+extern "C" int srm_label_jfa(srm_ctx *c, const int *steps, int nsteps, short *out, int on_device) {
+    int rc = require_ready(c, "srm_label_jfa", false);
+    if (rc) return rc;
+    if (!steps || nsteps <= 0 || !out) return fail(SRM_ERR_ARG, "srm_label_jfa: bad argument");
+    if (c->g.row0 != 0 || c->g.row1 != c->g.n) return fail(SRM_ERR_ARG, "srm_label_jfa: whole-grid contexts only");
+    CK(cudaSetDevice(c->device));
+    if (!c->labels) CK(cudaMalloc(&c->labels, c->N * sizeof(int)));
+    if (!c->scratch_map) CK(cudaMalloc(&c->scratch_map, c->N * sizeof(int)));
+    int *a = c->scratch_map, *b = c->labels;
+    srm_launch_fill_int(c->stream, a, c->N, SRM_SENT);
+    srm_launch_scatter_sites(c->stream, c->sites[current_buffer(c)], c->ctl, c->Kcap, c->g.n, a);
+    for (int s = 0; s < nsteps; ++s) {
+        if (steps[s] <= 0) return fail(SRM_ERR_ARG, "srm_label_jfa: step %d", steps[s]);
+        srm_launch_jfa_pass(c->stream, a, b, c->g.n, steps[s]);
+        std::swap(a, b);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, a, c->N * sizeof(int), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return SRM_OK;
+}
+
+// ------------------------------------------------------------------ one-shot drop-ins
+
+extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
+                        srm_stats *stats) {
+    if (!voronoi || !density) return fail(SRM_ERR_ARG, "srm_gcvt: null argument");
+    if (!valid_n(n)) return fail(SRM_ERR_ARG, "srm_gcvt: n=%d unsupported", n);
+    (void)depth;  // single level; see DESIGN.md (gcvt.h cannot drive depth > 1 either)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    srm_ctx *c = nullptr;
+    int rc = srm_create(&c, n, 0, n, dev);
+    if (rc) return rc;
+    rc = srm_set_density(c, density, 0);
+    if (!rc) rc = srm_set_mask(c, mask, 0);
+    if (!rc) rc = srm_set_site_map(c, voronoi, 0);
+    if (!rc) rc = srm_run(c, max_iter, 1, stats);
+    if (!rc) rc = srm_get_labels(c, voronoi, 0);
+    srm_destroy(c);
+    return rc;
+}
+
+extern "C" int srm_discretize(const double *points, const double *weight, int num_point, const int *triangle,
+                              int num_tri, float *density, double scale, int n) {
+    if (!points || !weight || (!triangle && num_tri > 0) || !density || num_point <= 0 || num_tri < 0)
+        return fail(SRM_ERR_ARG, "srm_discretize: bad argument");
+    if (n < 16 || (n % 16)) return fail(SRM_ERR_ARG, "srm_discretize: n=%d must be a multiple of 16", n);
+    if (!(scale > 0)) return fail(SRM_ERR_ARG, "srm_discretize: scale must be > 0");
+    for (int i = 0; i < 3 * num_tri; ++i)
+        if (triangle[i] < 0 || triangle[i] >= num_point) return fail(SRM_ERR_ARG, "srm_discretize: vertex index out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRM_ERR_CUDA, "srm_discretize: no CUDA device (libsrm has no CPU fallback)");
+    double *dp = nullptr, *dw = nullptr;
+    int *dt = nullptr;
+    float *dd = nullptr;
+    int rc = SRM_OK;
+    cudaError_t e;
+#define CKR(call) do { e = (call); if (e != cudaSuccess) { rc = fail(SRM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e)); goto out; } } while (0)
+    CKR(cudaMalloc(&dp, sizeof(double) * 2 * num_point));
+    CKR(cudaMalloc(&dw, sizeof(double) * num_point));
+    CKR(cudaMalloc(&dt, sizeof(int) * 3 * (size_t)(num_tri > 0 ? num_tri : 1)));
+    CKR(cudaMalloc(&dd, sizeof(float) * (size_t)n * n));
+    CKR(cudaMemcpy(dp, points, sizeof(double) * 2 * num_point, cudaMemcpyHostToDevice));
+    CKR(cudaMemcpy(dw, weight, sizeof(double) * num_point, cudaMemcpyHostToDevice));
+    if (num_tri > 0) CKR(cudaMemcpy(dt, triangle, sizeof(int) * 3 * (size_t)num_tri, cudaMemcpyHostToDevice));
+    CKR(srm_raster(nullptr, dp, dw, num_point, dt, num_tri, dd, scale, n));
+    CKR(cudaMemcpy(density, dd, sizeof(float) * (size_t)n * n, cudaMemcpyDeviceToHost));
+#undef CKR
+out:
+    cudaFree(dp); cudaFree(dw); cudaFree(dt); cudaFree(dd);
+    return rc;
+}
+
+// putConstrains + randomPoints (gcvt.h:58-122).  Host code in the reference too; the RNG is the
+// never-seeded KISS generator, which degenerates to the LCG j <- 69069 j + 1234567 on 64-bit
+// unsigned long.  Attempts are capped so that an unsatisfiable request fails
+// instead of spinning forever like the reference would.
+extern "C" int srm_seed(short *voronoi, const float *density, const unsigned char *mask, int num, int n,
+                        unsigned long long *rng_state) {
+    if (!voronoi || !density || n <= 0 || num < 0) return fail(SRM_ERR_ARG, "srm_seed: bad argument");
+    const size_t N = (size_t)n * n;
+    for (int y = 0; y < n; ++y)
+        for (int x = 0; x < n; ++x) {
+            const size_t i = (size_t)y * n + x;
+            const bool m = mask && mask[i];
+            voronoi[2 * i] = m ? (short)x : (short)SRM_MARKER;
+            voronoi[2 * i + 1] = m ? (short)y : (short)SRM_MARKER;
+        }
+    double mx = 0, avg = 0, cnt = 0;
+    for (size_t i = 0; i < N; ++i) {
+        if (density[i] > mx) mx = density[i];
+        if (density[i] != 0) { cnt += 1; avg += density[i]; }
+    }
+    mx = std::min(mx, avg / cnt * 100.);
+    unsigned long long j = rng_state ? *rng_state : 0ull;
+    auto next = [&j]() { j = 69069ull * j + 1234567ull; return (double)j / 18446744073709551616.0; };
+    const long long cap = 1000ll * (long long)num + 100000000ll;
+    long long attempts = 0;
+    for (int k = 0; k < num; ++k) {
+        for (;;) {
+            if (attempts++ >= cap) return fail(SRM_ERR_SEED, "srm_seed: placed %d of %d sites in %lld attempts", k, num, cap);
+            const int x = (int)(next() * n), y = (int)(next() * n);
+            const double z = next() * mx;
+            if (x >= n || y >= n) continue;
+            const size_t i = (size_t)y * n + x;
+            if (voronoi[2 * i] == SRM_MARKER && (double)density[i] > z) {
+                voronoi[2 * i] = (short)x;
+                voronoi[2 * i + 1] = (short)y;
+                break;
+            }
+        }
+    }
+    if (rng_state) *rng_state = j;
+    return SRM_OK;
+}
+
+extern "C" int srm_generate_mask(unsigned char *mask, const double *points_xy, int num_points, int n, double scale,
+                                 double left, double lower) {
+    if (!mask || (!points_xy && num_points > 0) || n <= 0) return fail(SRM_ERR_ARG, "srm_generate_mask: bad argument");
+    memset(mask, 0, (size_t)n * n);  // the reference clears 8 bytes and relies on fresh pages (gcvt.h:152)
+    for (int k = 0; k < num_points; ++k) {
+        const int x = (int)((points_xy[2 * k] - left) / scale), y = (int)((points_xy[2 * k + 1] - lower) / scale);
+        if (x < 0 || y < 0 || x >= n || y >= n) return fail(SRM_ERR_ARG, "srm_generate_mask: point %d outside the grid", k);
+        mask[(size_t)y * n + x] = 1;
+    }
+    return SRM_OK;
+}

@@ -1,0 +1,86 @@
+// srm_common.cuh — shared definitions of the sm_100a discrete-CVT engine (libsrm.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <limits.h>
+
+#define SRM_MARK (-32768)
+#define SRM_TIE_BAND_SHIFT 6   // 64-row bands of the reference's phase 1 (n/m1 == 64, gcvt.cu:842-847)
+#define SRM_BIG 40000          // "no site in this column" distance; > any real |dy| (<= 32767), BIG^2+225 < 2^31
+#define SRM_SENT ((int)0x80008000)  // (MARK,MARK) packed
+
+// Device-side loop state (gcvt.cu:1105-1142 keeps these on the host; here the host never syncs).
+struct SrmCtl {
+    int K;          // live sites
+    int Knext;      // written by the update compaction, latched by k_control
+    int stop;       // reference stopping rule fired
+    int it;         // iterations done (gcvtIterations)
+    float omega;    // pbaOmega
+    float lastE;    // lastEnergy
+    float E;        // Energy (float like the reference)
+    int pad;
+};
+
+__host__ __device__ __forceinline__ int srm_pack(int x, int y) { return (x & 0xffff) | (y << 16); }
+__host__ __device__ __forceinline__ int srm_x(int p) { return (int)(short)(p & 0xffff); }
+__host__ __device__ __forceinline__ int srm_y(int p) { return p >> 16; }
+
+// Column candidate (semantics of kernelFloodDown/Up + kernelPropagateInterband +
+// kernelUpdateVertical, gcvt.cu:77-216): U = nearest site row <= Y, D = nearest site row > Y.
+__device__ __forceinline__ int srm_choose_col(int U, int D, int Y) {
+    if (U == SRM_MARK) return D;
+    if (D == SRM_MARK) return U;
+    int du = Y - U, dd = D - Y;
+    if (du < dd) return U;
+    if (dd < du) return D;
+    return ((D >> SRM_TIE_BAND_SHIFT) == (Y >> SRM_TIE_BAND_SHIFT)) ? D : U;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += y;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- launchers (host), one per pipeline stage; all asynchronous on `st`.
+struct SrmGrid {           // geometry of one context
+    int n, row0, row1;
+    int nrows() const { return row1 - row0; }
+};
+
+void srm_launch_bits(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
+                     int *claim, int respect_stop);
+void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
+                      int respect_stop);
+void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
+                    const SrmCtl *ctl, int respect_stop);
+cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const SrmCtl *ctl,
+                           int respect_stop);
+cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels);
+cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes
+
+void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX);
+void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
+                    const int *idmap, SrmGrid g, double *acc, int Kcap, const SrmCtl *ctl, int want_energy,
+                    int respect_stop);
+void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
+                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int *blockcnt,
+                       int *blockoff, int want_energy, int stop_rule, int respect_stop);
+void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
+                               int *blockoff, SrmCtl *ctl, int count_only);
+void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out);
+void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step);
+void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map);
+void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value);
+
+cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int num_point, const int *tri, int num_tri,
+                       float *density, double scale, int n);

@@ -1,0 +1,440 @@
+// srm_label.cu — exact Voronoi labelling of a site set on an n x n grid, sm_100a.
+//
+// Replaces the reference's pba2DCompute (gcvt.cu:921-978: 9 kernels, ~48 B/px, pointer-chasing
+// stacks in global memory) with a from-scratch formulation that produces bit-identical labels
+// (rule: SURVEY Appendix A2) but never materialises a dense label map inside the Lloyd loop:
+//
+//   sites (K packed int32) --k_bits--> column bitmap  bits[(y>>5)*n + x] bit (y&31)     N/8 B
+//   k_carry: per column, nearest site row above / below every 32-row word                N/8 B
+//   k_col:   cy[Y][x] = row of the column candidate c(x,Y)                               2 B/px
+//   k_row:   per row, lower envelope of the parabolas (X-x)^2+(cy[x]-Y)^2 with INTEGER
+//            breakpoints -> run-length labels  rle[row] = {(site, first X)}             ~8 B/run
+//   k_expand (final labelling only): runs -> dense short2 labels                         4 B/px
+//
+// All arithmetic is integer; ties follow the reference (column tie: gcvt.cu:97-119 + :172-216;
+// row tie -> smallest x: gcvt.cu:449-466).
+#include "srm_common.cuh"
+
+// ------------------------------------------------------------------ sites -> bitmap
+
+__global__ void k_bits(const int *__restrict__ sites, const SrmCtl *__restrict__ ctl, int n, uint32_t *bits,
+                       int *idmap, int *claim, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ctl->K) return;
+    int p = sites[id];
+    int x = srm_x(p), y = srm_y(p);
+    atomicOr(&bits[(size_t)(y >> 5) * n + x], 1u << (y & 31));
+    size_t i = (size_t)y * n + x;
+    idmap[i] = id;      // site pixel -> accumulator slot
+    claim[i] = INT_MAX; // reset the dedupe claim left by the previous update
+}
+
+void srm_launch_bits(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
+                     int *claim, int respect_stop) {
+    // the memset is skipped after a stop only in effect (bits are then unused until the final labelling
+    // rebuilds them), so it can stay unconditional
+    cudaMemsetAsync(bits, 0, (size_t)(n >> 5) * n * sizeof(uint32_t), st);
+    if (Kcap > 0) k_bits<<<(Kcap + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop);
+}
+
+// Per column: up[j][x] = largest site row < 32j, dn[j][x] = smallest site row >= 32(j+1) (MARK if none).
+// This is the in-GPU analogue of kernelPropagateInterband (gcvt.cu:121-170) and, for row-band
+// sharding, what makes halo exchange unnecessary: every band scans the replicated bitmap.
+__global__ void k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up, short *__restrict__ dn,
+                        const SrmCtl *__restrict__ ctl, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= n) return;
+    int nw = n >> 5;
+    if (blockIdx.y == 0) {
+        int last = SRM_MARK;
+#pragma unroll 8
+        for (int j = 0; j < nw; ++j) {
+            size_t o = (size_t)j * n + x;
+            uint32_t w = bits[o];
+            up[o] = (short)last;
+            if (w) last = 32 * j + 31 - __clz(w);
+        }
+    } else {
+        int next = SRM_MARK;
+#pragma unroll 8
+        for (int j = nw - 1; j >= 0; --j) {
+            size_t o = (size_t)j * n + x;
+            uint32_t w = bits[o];
+            dn[o] = (short)next;
+            if (w) next = 32 * j + __ffs(w) - 1;
+        }
+    }
+}
+
+void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
+                      int respect_stop) {
+    dim3 grid((n + 63) / 64, 2);
+    k_carry<<<grid, 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop);
+}
+
+// cy[Y - row0][x] for the 32 rows of word-row j.
+__global__ void k_col(const uint32_t *__restrict__ bits, const short *__restrict__ up, const short *__restrict__ dn,
+                      int n, int row0, short *__restrict__ cy, const SrmCtl *__restrict__ ctl, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y + (row0 >> 5);
+    if (x >= n) return;
+    size_t o = (size_t)j * n + x;
+    uint32_t w = bits[o];
+    int U0 = up[o], D0 = dn[o];
+    short *out = cy + (size_t)(32 * j - row0) * n + x;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        int Y = 32 * j + k;
+        uint32_t mlo = w & (0xffffffffu >> (31 - k));
+        uint32_t mhi = (k == 31) ? 0u : (w & (0xffffffffu << (k + 1)));
+        int U = mlo ? 32 * j + 31 - __clz(mlo) : U0;
+        int D = mhi ? 32 * j + __ffs(mhi) - 1 : D0;
+        out[(size_t)k * n] = (short)srm_choose_col(U, D, Y);
+    }
+}
+
+void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
+                    const SrmCtl *ctl, int respect_stop) {
+    dim3 grid((g.n + 127) / 128, g.nrows() >> 5);
+    k_col<<<grid, 128, 0, st>>>(bits, up, dn, g.n, g.row0, cy, ctl, respect_stop);
+}
+
+// ------------------------------------------------------------------ row envelope
+
+#define ROW_NT 128
+#define ROW_NW (ROW_NT / 32)
+
+struct RowSmem {
+    unsigned short *lx;  // candidate column
+    short *lc;           // its site row c(x,Y)
+    short *lS;           // element wins for X > lS (within its merged group); -1 at the bottom
+    unsigned short *sb, *se;  // per-thread segment [sb,se)
+};
+
+__device__ __forceinline__ int min8_dist(uint4 v, int Y, int *g, short *cs) {
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    int M = SRM_BIG;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        short c = (short)((wv[k >> 1] >> ((k & 1) * 16)) & 0xffff);
+        int d = (c == SRM_MARK) ? SRM_BIG : abs((int)c - Y);
+        if (cs) { cs[k] = c; g[k] = d; }
+        M = min(M, d);
+    }
+    return M;
+}
+
+// Bridge two envelopes: segments [g0,gm) hold the left group, [gm,g1) the right group.
+// Pops dominated elements from the top of L and the bottom of R (PBA's band merge, gcvt.cu:293-410,
+// restated over integer breakpoints and contiguous smem segments).
+__device__ void merge_groups(const RowSmem &s, int g0, int gm, int g1, int Y, int n) {
+    int sl = gm - 1;
+    while (sl >= g0 && s.sb[sl] == s.se[sl]) --sl;
+    int sr = gm;
+    while (sr < g1 && s.sb[sr] == s.se[sr]) ++sr;
+    if (sl < g0 || sr >= g1) return;
+    int l = s.se[sl] - 1, r = s.sb[sr];
+    for (;;) {
+        int xl = s.lx[l], xr = s.lx[r];
+        int gl = s.lc[l] - Y, gr = s.lc[r] - Y;
+        int num = (xr * xr + gr * gr) - (xl * xl + gl * gl);
+        int den = 2 * (xr - xl);
+        if (num < ((int)s.lS[l] + 1) * den) {  // floor(num/den) <= S_l : l wins nowhere
+            s.se[sl] = (unsigned short)l;
+            if (l == s.sb[sl]) {
+                do { --sl; } while (sl >= g0 && s.sb[sl] == s.se[sl]);
+                if (sl < g0) { s.lS[r] = -1; return; }
+            }
+            l = s.se[sl] - 1;
+            continue;
+        }
+        bool rdead = num >= (n - 1) * den;  // r beats l only beyond the grid
+        if (!rdead) {
+            int r2 = -1;
+            if (r + 1 < s.se[sr]) r2 = r + 1;
+            else {
+                int s2 = sr + 1;
+                while (s2 < g1 && s.sb[s2] == s.se[s2]) ++s2;
+                if (s2 < g1) r2 = s.sb[s2];
+            }
+            if (r2 >= 0 && num >= (int)s.lS[r2] * den) rdead = true;  // floor(num/den) >= S_r2
+        }
+        if (rdead) {
+            s.sb[sr] = (unsigned short)(r + 1);
+            if (s.sb[sr] == s.se[sr]) {
+                do { ++sr; } while (sr < g1 && s.sb[sr] == s.se[sr]);
+                if (sr >= g1) return;
+            }
+            r = s.sb[sr];
+            continue;
+        }
+        s.lS[r] = (short)(num / den);  // num >= 0 here
+        return;
+    }
+}
+
+// One CTA per row.  P1: prune columns that are dominated from both sides by a neighbouring 8-column
+// block (sound: SURVEY Appendix B / DESIGN.md §row pass), compact the survivors.  P2: per-thread
+// stacks over short segments + log2(128) bridging levels.  P3: compact the envelope to global.
+__global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, int n, int row0, int2 *__restrict__ rle,
+                                                int *__restrict__ rle_cnt, const SrmCtl *__restrict__ ctl,
+                                                int respect_stop) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
+    __shared__ int wtot[ROW_NW];
+    if (respect_stop && ctl->stop) return;
+    RowSmem s;
+    s.lx = (unsigned short *)smem_raw;
+    s.lc = (short *)(s.lx + n);
+    s.lS = s.lc + n;
+    s.sb = sb_;
+    s.se = se_;
+
+    const int r = blockIdx.x, Y = row0 + r, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const short *row = cy + (size_t)r * n;
+    const int nchunks = n >> 8;
+    const int c0 = (w * nchunks) / ROW_NW, c1 = ((w + 1) * nchunks) / ROW_NW;
+    const int rb = c0 << 8;
+    int base = rb, carryM = SRM_BIG;
+
+    for (int c = c0; c < c1; ++c) {
+        const int x0 = (c << 8) + lane * 8;
+        int g[8];
+        short cs[8];
+        uint4 v = *reinterpret_cast<const uint4 *>(row + x0);
+        int M = min8_dist(v, Y, g, cs);
+        int ML = __shfl_up_sync(0xffffffffu, M, 1), MR = __shfl_down_sync(0xffffffffu, M, 1);
+        if (lane == 0) {
+            if (c == c0) {
+                ML = SRM_BIG;
+                if (x0 > 0) ML = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 - 8), Y, nullptr, nullptr);
+            } else ML = carryM;
+        }
+        if (lane == 31) {
+            MR = SRM_BIG;
+            if (x0 + 8 < n) MR = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 + 8), Y, nullptr, nullptr);
+        }
+        carryM = __shfl_sync(0xffffffffu, M, 31);
+        const int TL = ML * ML + 225, TR = MR * MR + 225;  // 15^2: farthest column of an adjacent block
+        unsigned live = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int g2 = g[k] * g[k];
+            bool dead = (g[k] == SRM_BIG) || (g2 >= TL && g2 > TR);
+            live |= dead ? 0u : (1u << k);
+        }
+        int cnt = __popc(live);
+        int incl = warp_incl_scan(cnt, lane);
+        int o = base + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (live & (1u << k)) { s.lx[o] = (unsigned short)(x0 + k); s.lc[o] = cs[k]; ++o; }
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+
+    // P2a: per-lane stack, in place over its slice of the warp's survivors
+    {
+        const int m = base - rb, q = (m + 31) >> 5;
+        const int beg = rb + min(lane * q, m), end = rb + min((lane + 1) * q, m);
+        int top = beg;
+        for (int i = beg; i < end; ++i) {
+            const int xr = s.lx[i];
+            const short cr = s.lc[i];
+            const int gr = cr - Y, Hr = xr * xr + gr * gr;
+            int num = 0, den = 1;
+            while (top > beg) {
+                int xl = s.lx[top - 1], gl = s.lc[top - 1] - Y;
+                num = Hr - (xl * xl + gl * gl);
+                den = 2 * (xr - xl);
+                if (num < ((int)s.lS[top - 1] + 1) * den) --top; else break;
+            }
+            short S = -1;
+            if (top > beg) {
+                if (num >= (n - 1) * den) continue;  // never wins inside the grid
+                S = (short)(num / den);
+            }
+            s.lx[top] = (unsigned short)xr; s.lc[top] = cr; s.lS[top] = S;
+            ++top;
+        }
+        s.sb[t] = (unsigned short)beg;
+        s.se[t] = (unsigned short)top;
+    }
+    __syncthreads();
+
+    // P2b: bridge neighbouring groups, doubling the group size each level
+    for (int span = 1; span < ROW_NT; span <<= 1) {
+        if ((t & (2 * span - 1)) == span) merge_groups(s, t - span, t, t + span, Y, n);
+        __syncthreads();
+    }
+
+    // P3: compact to global run-length form
+    {
+        const int b = s.sb[t], e = s.se[t], cnt = e - b;
+        int incl = warp_incl_scan(cnt, lane);
+        if (lane == 31) wtot[w] = incl;
+        __syncthreads();
+        int off = incl - cnt;
+        for (int k = 0; k < w; ++k) off += wtot[k];
+        int2 *out = rle + (size_t)r * n + off;
+        for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.lx[i], s.lc[i]), (int)s.lS[i] + 1);
+        if (t == ROW_NT - 1) rle_cnt[r] = off + cnt;
+    }
+}
+
+static size_t row_smem_bytes(int n) { return (size_t)n * 6; }
+
+cudaError_t srm_label_setup(int n) {
+    cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(n));
+    return e;
+}
+
+cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const SrmCtl *ctl,
+                           int respect_stop) {
+    k_row<<<g.nrows(), ROW_NT, row_smem_bytes(g.n), st>>>(cy, g.n, g.row0, rle, rle_cnt, ctl, respect_stop);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ runs -> dense labels
+
+#define EXP_NT 256
+// One CTA per row: scatter the run heads into a shared row, then a "last valid value" scan.
+__global__ void __launch_bounds__(EXP_NT) k_expand(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt, int n,
+                                                   int *__restrict__ labels) {
+    extern __shared__ __align__(16) int buf[];
+    __shared__ int wlast[EXP_NT / 32];
+    const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int cnt = rle_cnt[r];
+    const int2 *rr = rle + (size_t)r * n;
+    for (int i = t; i < n; i += EXP_NT) buf[i] = SRM_SENT;
+    __syncthreads();
+    for (int e = t; e < cnt; e += EXP_NT) { int2 v = rr[e]; buf[v.y] = v.x; }
+    __syncthreads();
+    int carry = SRM_SENT;
+    int4 *out = reinterpret_cast<int4 *>(labels + (size_t)r * n);
+    for (int base = 0; base < n; base += 4 * EXP_NT) {
+        const int q = (base >> 2) + t;
+        const bool in = (q << 2) < n;
+        int4 v = in ? reinterpret_cast<int4 *>(buf)[q] : make_int4(SRM_SENT, SRM_SENT, SRM_SENT, SRM_SENT);
+        int last = v.w != SRM_SENT ? v.w : v.z != SRM_SENT ? v.z : v.y != SRM_SENT ? v.y : v.x;
+        int x = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o && x == SRM_SENT) x = y;
+        }
+        int excl = __shfl_up_sync(0xffffffffu, x, 1);
+        if (lane == 0) excl = SRM_SENT;
+        if (lane == 31) wlast[w] = x;
+        __syncthreads();
+        int cw = carry;
+        for (int k = 0; k < w; ++k) if (wlast[k] != SRM_SENT) cw = wlast[k];
+        int inval = excl != SRM_SENT ? excl : cw;
+        if (v.x == SRM_SENT) v.x = inval;
+        if (v.y == SRM_SENT) v.y = v.x;
+        if (v.z == SRM_SENT) v.z = v.y;
+        if (v.w == SRM_SENT) v.w = v.z;
+        if (in) out[q] = v;
+        for (int k = 0; k < EXP_NT / 32; ++k) if (wlast[k] != SRM_SENT) carry = wlast[k];
+        __syncthreads();
+    }
+}
+
+cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels) {
+    size_t sm = (size_t)g.n * sizeof(int);
+    static int configured_for = 0;
+    if (sm > 48 * 1024 && configured_for < g.n) {
+        cudaError_t e = cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        configured_for = g.n;
+    }
+    k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, rle_cnt, g.n, labels);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ jump flooding (north_star family)
+
+// One JFA pass with step k: 3x3 stencil at +-k, key (dist^2, x, y).  Not the reference's algorithm
+// (SURVEY F1); pinned to oracle/srm_oracle.c:orc_label_jfa.  4 pixels per thread, 128-bit stores;
+// the centre row load is 128-bit, the +-k column loads are 128-bit when k % 4 == 0.
+__device__ __forceinline__ void jfa_take(int cand, int X, int Y, int &best, unsigned &bd) {
+    if (cand == SRM_SENT) return;
+    int sx = srm_x(cand), sy = srm_y(cand);
+    int dx = sx - X, dy = sy - Y;
+    unsigned d = (unsigned)(dx * dx + dy * dy);
+    if (best == SRM_SENT || d < bd) { best = cand; bd = d; return; }
+    if (d == bd) {
+        int bx = srm_x(best), by = srm_y(best);
+        if (sx < bx || (sx == bx && sy < by)) best = cand;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_jfa(const int *__restrict__ in, int *__restrict__ out, int n, int k) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 pixels
+    const int X0 = (q << 2) % n, Y = (q << 2) / n;
+    if (Y >= n) return;
+    int best[4] = {SRM_SENT, SRM_SENT, SRM_SENT, SRM_SENT};
+    unsigned bd[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int j = -1; j <= 1; ++j) {
+        const int qy = Y + j * k;
+        if (qy < 0 || qy >= n) continue;
+        const int *rowp = in + (size_t)qy * n;
+#pragma unroll
+        for (int i = -1; i <= 1; ++i) {
+            const int qx0 = X0 + i * k;
+            if ((k & 3) == 0 || i == 0) {
+                if (qx0 < 0 || qx0 + 3 >= n) {
+                    if (qx0 + 3 < 0 || qx0 >= n) continue;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        if (qx0 + p >= 0 && qx0 + p < n) jfa_take(rowp[qx0 + p], X0 + p, Y, best[p], bd[p]);
+                } else {
+                    int4 v = *reinterpret_cast<const int4 *>(rowp + qx0);
+                    jfa_take(v.x, X0, Y, best[0], bd[0]);
+                    jfa_take(v.y, X0 + 1, Y, best[1], bd[1]);
+                    jfa_take(v.z, X0 + 2, Y, best[2], bd[2]);
+                    jfa_take(v.w, X0 + 3, Y, best[3], bd[3]);
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (qx0 + p >= 0 && qx0 + p < n) jfa_take(__ldg(rowp + qx0 + p), X0 + p, Y, best[p], bd[p]);
+            }
+        }
+    }
+    *reinterpret_cast<int4 *>(out + (size_t)Y * n + X0) = make_int4(best[0], best[1], best[2], best[3]);
+}
+
+void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step) {
+    size_t groups = (size_t)n * n / 4;
+    k_jfa<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(in, out, n, step);
+}
+
+__global__ void k_scatter_sites(const int *__restrict__ sites, const SrmCtl *__restrict__ ctl, int n, int *map) {
+    int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ctl->K) return;
+    int p = sites[id];
+    map[(size_t)srm_y(p) * n + srm_x(p)] = p;
+}
+
+void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map) {
+    if (Kcap > 0) k_scatter_sites<<<(Kcap + 255) / 256, 256, 0, st>>>(sites, ctl, n, map);
+}
+
+__global__ void k_fill_int(int4 *p, size_t count4, int value) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    int4 v = make_int4(value, value, value, value);
+    for (; i < count4; i += stride) p[i] = v;
+}
+
+void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value) {
+    size_t c4 = count / 4;
+    unsigned blocks = (unsigned)((c4 + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_fill_int<<<blocks, 256, 0, st>>>(reinterpret_cast<int4 *>(p), c4, value);
+}

@@ -1,0 +1,329 @@
+// srm_lloyd.cu — centroid reduction, site update, energy/convergence control, sm_100a.
+//
+// Replaces pbaCVDComputeWeightedPrefix / pbaCVDComputeCentroid / pbaCVDUpdateSites /
+// pbaCVDCalcEnergy and the control block of gCVT (gcvt.cu:995-1034, 1059-1083, 1105-1142).
+//
+// Design: the density never changes during a gCVT call, so (like the reference, gcvt.cu:514-560,
+// but in fp64 instead of fp32) the row-inclusive prefix sums of d, x*d and x^2*d are built once.
+// A Lloyd iteration then needs NO per-pixel work for the centroid: every run of the run-length
+// labels contributes prefix[end] - prefix[start-1] to its site (sum y*d = Y * sum d within a row),
+// and the CVT energy follows from the same three sums.  Accumulators are fp64 per site
+// (W, X, Y, pad) and are all-reduced across row bands by the caller when sharded.
+#include "srm_common.cuh"
+
+// ------------------------------------------------------------------ prefix sums (once per call)
+
+#define PFX_NT 256
+__global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ density, int n, double2 *__restrict__ P2,
+                                                   double *__restrict__ PXX) {
+    __shared__ double sw[3][PFX_NT / 32];
+    const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const float *d = density + (size_t)r * n;
+    double cW = 0, cX = 0, cXX = 0;
+    for (int base = 0; base < n; base += 4 * PFX_NT) {
+        const int x = base + 4 * t;
+        const bool in = x < n;
+        float4 v = in ? *reinterpret_cast<const float4 *>(d + x) : make_float4(0, 0, 0, 0);
+        double a[4] = {v.x, v.y, v.z, v.w};
+        double W[4], X[4], XX[4];
+        double rw = 0, rx = 0, rxx = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double px = (double)(x + k);
+            rw += a[k]; rx += px * a[k]; rxx += px * px * a[k];
+            W[k] = rw; X[k] = rx; XX[k] = rxx;
+        }
+        double iw = rw, ix = rx, ixx = rxx;  // warp inclusive scan of the per-thread totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double yw = __shfl_up_sync(0xffffffffu, iw, o), yx = __shfl_up_sync(0xffffffffu, ix, o),
+                   yxx = __shfl_up_sync(0xffffffffu, ixx, o);
+            if (lane >= o) { iw += yw; ix += yx; ixx += yxx; }
+        }
+        if (lane == 31) { sw[0][w] = iw; sw[1][w] = ix; sw[2][w] = ixx; }
+        __syncthreads();
+        double ew = cW + (iw - rw), ex = cX + (ix - rx), exx = cXX + (ixx - rxx);
+        double tw = 0, tx = 0, txx = 0;
+#pragma unroll
+        for (int k = 0; k < PFX_NT / 32; ++k) {
+            if (k < w) { ew += sw[0][k]; ex += sw[1][k]; exx += sw[2][k]; }
+            tw += sw[0][k]; tx += sw[1][k]; txx += sw[2][k];
+        }
+        if (in) {
+            size_t o = (size_t)r * n + x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                P2[o + k] = make_double2(ew + W[k], ex + X[k]);
+                PXX[o + k] = exx + XX[k];
+            }
+        }
+        cW += tw; cX += tx; cXX += txx;
+        __syncthreads();
+    }
+}
+
+void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX) {
+    k_prefix<<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
+}
+
+// ------------------------------------------------------------------ per-run accumulation
+
+#define ACC_NT 128
+// One warp per row; lanes stride over the row's runs.
+__global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt,
+                                                const double2 *__restrict__ P2, const double *__restrict__ PXX,
+                                                const int *__restrict__ idmap, int n, int row0, int nrows,
+                                                double *__restrict__ acc, int Kcap, const SrmCtl *__restrict__ ctl,
+                                                int want_energy, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5);
+    if (r >= nrows) return;
+    const int Y = row0 + r, cnt = rle_cnt[r];
+    const int2 *rr = rle + (size_t)r * n;
+    const double2 *p2 = P2 + (size_t)r * n;
+    const double *pxx = PXX + (size_t)r * n;
+    double e_loc = 0;
+    double2 carry = make_double2(0, 0);  // prefix at the end of the previous run
+    double carryxx = 0;
+    for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        const bool act = e < cnt;
+        int2 v = act ? rr[e] : make_int2(0, 0);
+        int b = n - 1;
+        if (act && e + 1 < cnt) b = rr[e + 1].y - 1;
+        double2 pb = act ? p2[b] : make_double2(0, 0);
+        double xb = (act && want_energy) ? pxx[b] : 0;
+        double2 pa;
+        pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1);
+        pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);
+        double xa = __shfl_up_sync(0xffffffffu, xb, 1);
+        if (lane == 0) { pa = carry; xa = carryxx; }
+        // last active lane's pb is the carry for the next batch of 32 runs
+        int lastl = min(31, cnt - e0 - 1);
+        carry.x = __shfl_sync(0xffffffffu, pb.x, lastl);
+        carry.y = __shfl_sync(0xffffffffu, pb.y, lastl);
+        carryxx = __shfl_sync(0xffffffffu, xb, lastl);
+        if (act) {
+            const double W = pb.x - pa.x, X = pb.y - pa.y;
+            const int sx = srm_x(v.x), sy = srm_y(v.x);
+            const int id = idmap[(size_t)sy * n + sx];
+            double *a = acc + 4 * (size_t)id;
+            atomicAdd(a, W);
+            atomicAdd(a + 1, X);
+            atomicAdd(a + 2, (double)Y * W);
+            if (want_energy) {
+                const int dy = sy - Y;
+                e_loc += (xb - xa) - 2.0 * (double)sx * X + (double)(sx * sx + dy * dy) * W;
+            }
+        }
+    }
+    if (want_energy) {
+        e_loc = warp_sum(e_loc);
+        if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
+    }
+}
+
+void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
+                    const int *idmap, SrmGrid g, double *acc, int Kcap, const SrmCtl *ctl, int want_energy,
+                    int respect_stop) {
+    int rows_per_block = ACC_NT / 32;
+    k_acc<<<(g.nrows() + rows_per_block - 1) / rows_per_block, ACC_NT, 0, st>>>(
+        rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, ctl, want_energy, respect_stop);
+}
+
+// ------------------------------------------------------------------ block-count scan helper
+
+// Exclusive scan of nb block counts by one CTA; total -> *total_out.
+__global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cnt, int *__restrict__ off, int nb,
+                                                      int *total_out) {
+    __shared__ int ws[32];
+    __shared__ int carry_s;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += 1024) {
+        int i = base + t;
+        int v = i < nb ? cnt[i] : 0;
+        int incl = warp_incl_scan(v, lane);
+        if (lane == 31) ws[w] = incl;
+        __syncthreads();
+        int wo = 0, tot = 0;
+        for (int k = 0; k < 32; ++k) { if (k < w) wo += ws[k]; tot += ws[k]; }
+        int c = carry_s;
+        if (i < nb) off[i] = c + wo + incl - v;
+        __syncthreads();
+        if (t == 0) carry_s = c + tot;
+        __syncthreads();
+    }
+    if (t == 0) *total_out = carry_s;
+}
+
+void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out) {
+    k_scan_counts<<<1, 1024, 0, st>>>(cnt, off, nb, total_out);
+}
+
+// ------------------------------------------------------------------ site update
+
+// kernelUpdateSites (gcvt.cu:753-781): centroid, over-relaxation, round, clamp, reject.  The float
+// expression is written with the roundings nvcc produced for the reference (FADD, FFMA, FADD,
+// F2I.TRUNC; checked in the SASS of oracle/_ref).  Collisions: every site claims its target pixel
+// with atomicMin(id); the smallest id survives (the reference merges sites the same way, by
+// overwriting one pixel, gcvt.cu:779-780).
+__global__ void k_update_pos(const int *__restrict__ sites, const double *__restrict__ acc,
+                             const float *__restrict__ density, const unsigned char *__restrict__ mask, int n,
+                             const SrmCtl *__restrict__ ctl, int *__restrict__ newpos, int *claim, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ctl->K) return;
+    const int p = sites[id];
+    const int tx = srm_x(p), ty = srm_y(p);
+    int rx = tx, ry = ty;
+    if (!(mask && mask[(size_t)ty * n + tx])) {
+        const double *a = acc + 4 * (size_t)id;
+        const float pW = (float)a[0], pX = (float)a[1], pY = (float)a[2];
+        const float omega = ctl->omega;
+        const float _x = __fdiv_rn(pX, pW), _y = __fdiv_rn(pY, pW);
+        const float fx = __fadd_rn(__fmaf_rn(__fsub_rn(_x, (float)tx), omega, (float)tx), 0.5f);
+        const float fy = __fadd_rn(__fmaf_rn(__fsub_rn(_y, (float)ty), omega, (float)ty), 0.5f);
+        int cx = __float2int_rz(fx), cy = __float2int_rz(fy);  // NaN -> 0, like F2I.TRUNC
+        cx = max(min(cx, n - 1), 0);
+        cy = max(min(cy, n - 1), 0);
+        if (density[(size_t)cy * n + cx] != 0.0f) { rx = cx; ry = cy; }
+    }
+    newpos[id] = srm_pack(rx, ry);
+    atomicMin(&claim[(size_t)ry * n + rx], id);
+}
+
+#define UPD_NT 256
+__global__ void __launch_bounds__(UPD_NT) k_update_count(const int *__restrict__ newpos, const int *__restrict__ claim,
+                                                         int n, const SrmCtl *__restrict__ ctl, int *blockcnt,
+                                                         int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    const int id = blockIdx.x * UPD_NT + threadIdx.x;
+    int flag = 0;
+    if (id < ctl->K) {
+        int p = newpos[id];
+        flag = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
+    }
+    int c = __syncthreads_count(flag);
+    if (threadIdx.x == 0) blockcnt[blockIdx.x] = c;
+}
+
+__global__ void __launch_bounds__(UPD_NT) k_update_write(const int *__restrict__ newpos, const int *__restrict__ claim,
+                                                         int n, const SrmCtl *__restrict__ ctl,
+                                                         const int *__restrict__ blockoff, int *__restrict__ sites_out,
+                                                         double *__restrict__ acc, int respect_stop) {
+    __shared__ int wtot[UPD_NT / 32];
+    if (respect_stop && ctl->stop) return;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int id = blockIdx.x * UPD_NT + t;
+    int flag = 0, p = 0;
+    if (id < ctl->K) {
+        p = newpos[id];
+        flag = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
+        double *a = acc + 4 * (size_t)id;  // clear for the next iteration
+        a[0] = 0; a[1] = 0; a[2] = 0; a[3] = 0;
+    }
+    int incl = warp_incl_scan(flag, lane);
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    int off = blockoff[blockIdx.x] + incl - flag;
+    for (int k = 0; k < w; ++k) off += wtot[k];
+    if (flag) sites_out[off] = p;
+}
+
+// Loop control of gCVT (gcvt.cu:1116-1140), on device.  `it_done` = gcvtIterations after this iteration.
+__global__ void k_control(SrmCtl *ctl, double *acc_energy, int n, int want_energy, int stop_rule, int respect_stop) {
+    if (respect_stop && ctl->stop) return;
+    ctl->K = ctl->Knext;
+    if (want_energy) {
+        ctl->E = (float)(acc_energy[0] / ((double)n * (double)n));
+        acc_energy[0] = 0;
+    }
+    const int it = ctl->it + 1;
+    ctl->it = it;
+    if (it % 10 == 0) {
+        const float diffEnergy = ctl->lastE - ctl->E;
+        const float gradientEnergy = (float)((double)diffEnergy / 10.0);
+        const double om = 1.0 + (double)diffEnergy;
+        ctl->omega = (float)(om < 2.0 ? om : 2.0);
+        if (stop_rule && (double)gradientEnergy < 1e-5) ctl->stop = 1;
+        else ctl->lastE = ctl->E;
+    }
+}
+
+void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
+                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int *blockcnt,
+                       int *blockoff, int want_energy, int stop_rule, int respect_stop) {
+    if (Kcap > 0) {
+        const int nb = (Kcap + UPD_NT - 1) / UPD_NT;
+        k_update_pos<<<(Kcap + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim,
+                                                          respect_stop);
+        k_update_count<<<nb, UPD_NT, 0, st>>>(newpos, claim, n, ctl, blockcnt, respect_stop);
+        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, &ctl->Knext);
+        k_update_write<<<nb, UPD_NT, 0, st>>>(newpos, claim, n, ctl, blockoff, sites_out, acc, respect_stop);
+    }
+    k_control<<<1, 1, 0, st>>>(ctl, acc + 4 * (size_t)Kcap, n, want_energy, stop_rule, respect_stop);
+}
+
+// ------------------------------------------------------------------ dense seed map -> site list
+
+#define SFM_NT 256
+#define SFM_TILE (SFM_NT * 4)
+__device__ __forceinline__ int is_site4(int4 v, int *f) {
+    f[0] = (short)(v.x & 0xffff) != SRM_MARK;
+    f[1] = (short)(v.y & 0xffff) != SRM_MARK;
+    f[2] = (short)(v.z & 0xffff) != SRM_MARK;
+    f[3] = (short)(v.w & 0xffff) != SRM_MARK;
+    return f[0] + f[1] + f[2] + f[3];
+}
+
+// Sites of a seed map = pixels whose x half is not MARKER (gcvt.cu:90, :240), in scan order.
+__global__ void __launch_bounds__(SFM_NT) k_sites_count(const int4 *__restrict__ map4, size_t n4, int *blockcnt) {
+    __shared__ int ws[SFM_NT / 32];
+    size_t q = (size_t)blockIdx.x * SFM_NT + threadIdx.x;
+    int f[4], c = 0;
+    if (q < n4) c = is_site4(map4[q], f);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int k = 0; k < SFM_NT / 32; ++k) s += ws[k];
+        blockcnt[blockIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SFM_NT) k_sites_write(const int4 *__restrict__ map4, size_t n4,
+                                                        const int *__restrict__ blockoff, int *__restrict__ sites) {
+    __shared__ int ws[SFM_NT / 32];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    size_t q = (size_t)blockIdx.x * SFM_NT + t;
+    int f[4] = {0, 0, 0, 0}, c = 0;
+    int4 v = make_int4(0, 0, 0, 0);
+    if (q < n4) { v = map4[q]; c = is_site4(v, f); }
+    int incl = warp_incl_scan(c, lane);
+    if (lane == 31) ws[w] = incl;
+    __syncthreads();
+    int off = blockoff[blockIdx.x] + incl - c;
+    for (int k = 0; k < w; ++k) off += ws[k];
+    if (f[0]) sites[off++] = v.x;
+    if (f[1]) sites[off++] = v.y;
+    if (f[2]) sites[off++] = v.z;
+    if (f[3]) sites[off++] = v.w;
+}
+
+// count_only != 0: fill blockcnt/blockoff and ctl->Knext (the caller sizes the site arrays from it);
+// count_only == 0: blockoff must hold the scan; writes the list.
+void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
+                               int *blockoff, SrmCtl *ctl, int count_only) {
+    const size_t n4 = N / 4;
+    const int nb = (int)((n4 + SFM_NT - 1) / SFM_NT);
+    if (count_only) {
+        k_sites_count<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockcnt);
+        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, &ctl->Knext);
+    } else {
+        k_sites_write<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockoff, sites_out);
+    }
+}

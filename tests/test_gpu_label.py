@@ -1,0 +1,83 @@
+"""Parity of the CUDA labelling (through the C ABI) with the CPU oracle: bit-exact (integer work)."""
+import numpy as np
+import pytest
+
+import _inputs as I
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _label(seeds):
+    import surface_remesher_b200 as S
+    n = seeds.shape[0]
+    with S.Context(n) as c:
+        c.set_site_map(np.ascontiguousarray(seeds))
+        c.label()
+        return c.get_labels()
+
+
+@pytest.mark.parametrize("n,k,seed", [(256, 1, 0), (256, 2, 1), (256, 50, 2), (256, 4000, 3), (512, 500, 4),
+                                      (512, 20000, 5), (1024, 2000, 6), (768, 3000, 7), (2048, 10000, 8)])
+def test_label_random(n, k, seed):
+    seeds = I.random_sites(n, k, seed)
+    got = _label(seeds)
+    exp = O.label_exact(seeds)
+    bad = (got != exp).any(axis=2)
+    assert bad.sum() == 0, f"{bad.sum()} mismatching pixels, first at {np.argwhere(bad)[:5]}"
+
+
+@pytest.mark.parametrize("n,pitch,off", [(256, 8, 4), (256, 2, 0), (512, 16, 7), (512, 64, 31), (1024, 128, 64)])
+def test_label_lattice_ties(n, pitch, off):
+    seeds = I.lattice_sites(n, pitch, off)
+    got = _label(seeds)
+    exp = O.label_exact(seeds)
+    assert (got != exp).sum() == 0
+
+
+def test_label_degenerate_layouts():
+    n = 256
+    cases = []
+    v = np.full((n, n, 2), I.MARK, np.int16); v[100, :, 0] = np.arange(n); v[100, :, 1] = 100; cases.append(v)   # one full row
+    v = np.full((n, n, 2), I.MARK, np.int16); v[:, 17, 0] = 17; v[:, 17, 1] = np.arange(n); cases.append(v)       # one full column
+    v = np.full((n, n, 2), I.MARK, np.int16)
+    for i in range(n): v[i, i] = (i, i)
+    cases.append(v)                                                                                               # diagonal
+    v = np.full((n, n, 2), I.MARK, np.int16); v[0, 0] = (0, 0); v[n - 1, n - 1] = (n - 1, n - 1); cases.append(v)  # corners
+    v = np.full((n, n, 2), I.MARK, np.int16)
+    ys, xs = np.mgrid[0:n, 0:n]; v[..., 0] = xs; v[..., 1] = ys; cases.append(v)                                  # every pixel a site
+    for s in cases:
+        got = _label(s)
+        exp = O.label_brute(s)
+        assert (got != exp).sum() == 0
+
+
+def test_label_row_band_contexts_agree():
+    import surface_remesher_b200 as S
+    n = 512
+    seeds = I.random_sites(n, 3000, 11)
+    exp = O.label_exact(seeds)
+    for (r0, r1) in S.row_bands(n, 4):
+        with S.Context(n, r0, r1) as c:
+            c.set_site_map(np.ascontiguousarray(seeds))
+            c.label()
+            got = c.get_labels()
+        assert (got != exp[r0:r1]).sum() == 0
+
+
+def test_jfa_matches_cpu_jfa_and_error_rate():
+    import surface_remesher_b200 as S
+    n = 512
+    seeds = I.random_sites(n, 2000, 12)
+    steps = [1] + [n >> (i + 1) for i in range(int(np.log2(n)))]  # 1+JFA
+    with S.Context(n) as c:
+        c.set_site_map(np.ascontiguousarray(seeds))
+        got = c.label_jfa(steps)
+    exp = O.label_jfa(seeds, steps)
+    assert (got != exp).sum() == 0
+    exact = O.label_exact(seeds)
+    ys, xs = np.mgrid[0:n, 0:n]
+    d_j = (got[..., 0].astype(np.int64) - xs) ** 2 + (got[..., 1].astype(np.int64) - ys) ** 2
+    d_e = (exact[..., 0].astype(np.int64) - xs) ** 2 + (exact[..., 1].astype(np.int64) - ys) ** 2
+    assert (d_j < d_e).sum() == 0           # JFA can never beat the exact distance
+    assert (d_j > d_e).mean() < 1e-3        # and is wrong on well under 0.1 % of pixels
