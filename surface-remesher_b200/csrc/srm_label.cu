@@ -358,7 +358,7 @@ cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_c
 // ------------------------------------------------------------------ jump flooding (north_star family)
 
 // One JFA pass with step k: 3x3 stencil at +-k, key (dist^2, x, y).  Not the reference's algorithm
-// (SURVEY F1); pinned to oracle/srm_oracle.c:orc_label_jfa.  4 pixels per thread, 128-bit stores;
+// (SURVEY F1); pinned by the tests to a CPU JFA with the same schedule and key.  4 pixels per thread, 128-bit stores;
 // the centre row load is 128-bit, the +-k column loads are 128-bit when k % 4 == 0.
 __device__ __forceinline__ void jfa_take(int cand, int X, int Y, int &best, unsigned &bd) {
     if (cand == SRM_SENT) return;

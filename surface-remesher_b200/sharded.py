@@ -1,0 +1,105 @@
+"""Row-band sharding of one Lloyd loop over the GPUs of a node.
+
+One process per GPU.  Rank r owns rows [r*n/W, (r+1)*n/W).  Site list, site bitmap, density and mask
+are replicated; the labelling of a band needs no halo exchange because every rank scans the replicated
+column bitmap above and below its band (csrc/srm_label.cu:k_carry).  The only data-path collective is
+one all-reduce (sum, fp64) per iteration over the per-site accumulators (W, X, Y, 0) plus the energy
+scalar; the site update is then replicated on every rank, deterministically, so the site lists stay
+identical without a broadcast.
+
+The band engine is injected so that the host logic (partition, collective, schedule) is testable on
+CPU with the gloo backend (tests/test_dist_gloo.py uses an oracle-backed engine); the product engine
+is CudaBandEngine over libsrm.so.
+"""
+import numpy as np
+
+from .api import Context, row_bands
+
+
+class _CudaArray:
+    """__cuda_array_interface__ view of a raw device pointer (float64 vector)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class CudaBandEngine:
+    """libsrm.so context for one row band; all work is enqueued on torch's current CUDA stream."""
+
+    def __init__(self, n, row0, row1, device):
+        import torch
+        self.torch = torch
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.ctx = Context(n, row0, row1, device)
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._acc = None
+
+    def set_inputs(self, density, mask, site_map):
+        self.ctx.set_density(density)
+        self.ctx.set_mask(mask)
+        self.ctx.set_site_map(site_map)
+        ptr, cnt = self.ctx.acc_buffer()
+        self._keep = _CudaArray(ptr, cnt)
+        self._acc = self.torch.as_tensor(self._keep, device=self.device)
+
+    def set_sites(self, packed):
+        self.ctx.set_sites(packed)
+        ptr, cnt = self.ctx.acc_buffer()
+        self._keep = _CudaArray(ptr, cnt)
+        self._acc = self.torch.as_tensor(self._keep, device=self.device)
+
+    def label(self):
+        self.ctx.label()
+
+    def accumulate(self, want_energy):
+        self.ctx.accumulate(want_energy)
+
+    def acc_tensor(self):
+        return self._acc
+
+    def update(self):
+        self.ctx.update()
+
+    def sites(self):
+        return self.ctx.get_sites()
+
+    def labels(self):
+        return self.ctx.get_labels()
+
+    def state(self):
+        return self.ctx.state()
+
+    def close(self):
+        self.ctx.close()
+
+
+class ShardedLloyd:
+    """The Lloyd loop of gCVT (gcvt.cu:1110-1147, single level) over `world` row bands."""
+
+    def __init__(self, n, rank, world, engine, dist=None):
+        self.n, self.rank, self.world = n, rank, world
+        self.row0, self.row1 = row_bands(n, world)[rank]
+        self.engine = engine
+        self.dist = dist
+        self.it = 0
+
+    def step(self):
+        """label -> per-band accumulate -> all-reduce -> replicated update."""
+        want_energy = (self.it % 10) == 0   # gcvt.cu:1116
+        self.engine.label()
+        self.engine.accumulate(want_energy)
+        if self.world > 1:
+            self.dist.all_reduce(self.engine.acc_tensor())  # sum
+        self.engine.update()
+        self.it += 1
+
+    def run(self, iters):
+        for _ in range(iters):
+            self.step()
+
+    def final_labels(self):
+        """Labels of this band for the current sites (gcvt.cu:1149)."""
+        self.engine.label()
+        return self.engine.labels()

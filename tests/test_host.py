@@ -1,0 +1,100 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol include/srm.h declares,
+host-only entry points (seeding, mask) match the oracle, argument errors are reported, and compute entry
+points fail loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import _inputs as I
+import _oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import surface_remesher_b200 as S
+    hdr = open(os.path.join(ROOT, "include", "srm.h")).read()
+    names = sorted(set(re.findall(r"\b(srm_[a-z_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    L = C.CDLL(S.lib_path())
+    for nm in names:
+        assert hasattr(L, nm), nm
+
+
+def test_dropin_library_exports_reference_signatures():
+    so = os.path.join(ROOT, "surface-remesher_b200", "libsrm_dropin.so")
+    L = C.CDLL(so)
+    # mangled names of gCVT(short*,float*,bool*,int,int,int) and discretization_d(double*,double*,int,int*,int,float*,double,int)
+    assert hasattr(L, "_Z4gCVTPsPfPbiii")
+    assert hasattr(L, "_Z16discretization_dPdS_iPiiPfdi")
+
+
+@pytest.mark.parametrize("n,k,kind", [(256, 300, "c3"), (256, 1000, "uniform"), (512, 5000, "c3")])
+def test_seed_matches_oracle(n, k, kind):
+    import surface_remesher_b200 as S
+    dens = I.density_uniform(n) if kind == "uniform" else I.density_c3(n)
+    mask = None if kind == "uniform" else I.mask_c3(dens)
+    exp, att, st = O.seed(dens, mask, k)
+    vor = np.empty((n, n, 2), np.int16)
+    state = C.c_ulonglong(0)
+    rc = S.lib().srm_seed(vor.ctypes.data, dens.ctypes.data, None if mask is None else mask.ctypes.data, k, n,
+                          C.byref(state))
+    assert rc == 0
+    assert np.array_equal(vor, exp) and state.value == st
+
+
+def test_seed_reports_unsatisfiable_request():
+    import surface_remesher_b200 as S
+    n = 16
+    dens = np.zeros((n, n), np.float32); dens[3, 3] = 1
+    vor = np.empty((n, n, 2), np.int16)
+    rc = S.lib().srm_seed(vor.ctypes.data, dens.ctypes.data, None, 2, n, None)
+    assert rc == 4 and b"placed 1 of 2" in S.lib().srm_last_error()
+
+
+def test_generate_mask():
+    import surface_remesher_b200 as S
+    n = 64
+    m = np.ones((n, n), np.uint8)
+    pts = np.array([[0.0, 0.0], [0.5, 0.25], [0.999, 0.999]])
+    S.generateMask(pts, m, n, 1.0 / (n - 1), 0.0, 0.0)
+    assert m.sum() == 3 and m[0, 0] and m[int(0.25 * (n - 1)), int(0.5 * (n - 1))] and m[62, 62]
+    with pytest.raises(S.SrmError):
+        S.generateMask(np.array([[2.0, 0.0]]), m, n, 1.0 / (n - 1), 0.0, 0.0)
+
+
+def test_argument_errors():
+    import surface_remesher_b200 as S
+    L = S.lib()
+    h = C.c_void_p()
+    assert L.srm_create(C.byref(h), 100, 0, 100, 0) == 1          # n not a multiple of 256
+    assert L.srm_create(C.byref(h), 256, 0, 100, 0) == 1          # band not a multiple of 64
+    assert L.srm_gcvt(None, None, None, 256, 1, 10, None) == 1
+    d = np.zeros((16, 16), np.float32)
+    p = np.zeros((3, 2)); w = np.zeros(3); t = np.array([[0, 1, 7]], np.int32)
+    assert L.srm_discretize(p.ctypes.data, w.ctypes.data, 3, t.ctypes.data, 1, d.ctypes.data, 1.0, 16) == 1  # index out of range
+    assert L.srm_discretize(p.ctypes.data, w.ctypes.data, 3, t.ctypes.data, 0, d.ctypes.data, 0.0, 16) == 1  # scale
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import surface_remesher_b200 as S
+    with pytest.raises(S.SrmError, match="no CUDA device"):
+        S.Context(256)
+    v = np.full((256, 256, 2), -32768, np.int16); v[5, 5] = (5, 5)
+    with pytest.raises(S.SrmError):
+        S.gCVT(v, np.ones((256, 256), np.float32), None, 256, 1, 3)
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(ROOT, "surface-remesher_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
+                txt = open(os.path.join(dp, f)).read()
+                assert "liboracle" not in txt and "_oracle" not in txt and "orc_" not in txt, f
