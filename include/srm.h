@@ -103,6 +103,9 @@ int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
 /* iters x (label, accumulate, update) with the reference's energy/omega schedule; stop_rule != 0
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */
 int srm_iterate(srm_ctx *ctx, int iters, int stop_rule);
+/* Same loop with CUDA events between the stages (measurement only): stage_ms[6] receives the summed device
+ * milliseconds of {site bitmap + carries, column pass, row envelope, accumulate, update + control, whole iteration}. */
+int srm_iterate_profiled(srm_ctx *ctx, int iters, int stop_rule, float *stage_ms);
 /* Whole gCVT on resident inputs: loop + final labelling. */
 int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);
 int srm_get_state(srm_ctx *ctx, srm_stats *stats);

@@ -62,6 +62,7 @@ def lib():
     L.srm_update.argtypes = [p]
     L.srm_acc_buffer.argtypes = [p, C.POINTER(p), C.POINTER(C.c_size_t)]
     L.srm_iterate.argtypes = [p, i, i]
+    L.srm_iterate_profiled.argtypes = [p, i, i, p]
     L.srm_run.argtypes = [p, i, i, p]
     L.srm_get_state.argtypes = [p, p]
     L.srm_get_labels.argtypes = [p, p, i]
@@ -69,7 +70,7 @@ def lib():
     for name in ("srm_gcvt", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
                  "srm_set_stream", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_label", "srm_accumulate", "srm_update",
-                 "srm_acc_buffer", "srm_iterate", "srm_run", "srm_get_state", "srm_get_labels", "srm_label_jfa"):
+                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -250,6 +251,14 @@ class Context:
 
     def iterate(self, iters, stop_rule=False):
         _ck(lib().srm_iterate(self._h, int(iters), int(bool(stop_rule))))
+
+    STAGES = ("bitmap+carry", "column", "row_envelope", "accumulate", "update", "iteration")
+
+    def iterate_profiled(self, iters, stop_rule=False):
+        """dict stage -> summed device ms over `iters` iterations (CUDA events between the stages)."""
+        ms = (C.c_float * 6)()
+        _ck(lib().srm_iterate_profiled(self._h, int(iters), int(bool(stop_rule)), ms))
+        return dict(zip(self.STAGES, [float(v) for v in ms]))
 
     def run(self, max_iter, stop_rule=True):
         st = Stats()

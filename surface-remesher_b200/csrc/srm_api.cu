@@ -371,6 +371,57 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     return SRM_OK;
 }
 
+// Same loop as srm_iterate with CUDA events between the stages; stage_ms[6] receives the summed device
+// time of {site bitmap+carry, column pass, row envelope, accumulate, update+control, whole iteration}.
+extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float *stage_ms) {
+    int rc = require_ready(c, "srm_iterate_profiled", true);
+    if (rc) return rc;
+    if (!stage_ms || iters <= 0) return fail(SRM_ERR_ARG, "srm_iterate_profiled: bad argument");
+    CK(cudaSetDevice(c->device));
+    for (int k = 0; k < 6; ++k) stage_ms[k] = 0;
+    if (c->stopped) return SRM_OK;
+    std::vector<cudaEvent_t> ev((size_t)iters * 6);
+    for (auto &e : ev) CK(cudaEventCreate(&e));
+    int it = c->it_host;
+    for (int i = 0; i < iters; ++i, ++it) {
+        const int buf = it & 1, want_energy = (it % 10) == 0;
+        cudaEvent_t *e = &ev[(size_t)i * 6];
+        CK(cudaEventRecord(e[0], c->stream));
+        srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1);
+        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1);
+        CK(cudaEventRecord(e[1], c->stream));
+        srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, c->ctl, 1);
+        CK(cudaEventRecord(e[2], c->stream));
+        CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, c->ctl, 1));
+        CK(cudaEventRecord(e[3], c->stream));
+        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl,
+                       want_energy, 1);
+        CK(cudaEventRecord(e[4], c->stream));
+        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
+                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt,
+                          c->blockoff, want_energy, stop_rule, 1);
+        CK(cudaEventRecord(e[5], c->stream));
+    }
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < iters; ++i) {
+        cudaEvent_t *e = &ev[(size_t)i * 6];
+        for (int k = 0; k < 5; ++k) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e[k], e[k + 1]));
+            stage_ms[k] += ms;
+        }
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e[0], e[5]));
+        stage_ms[5] += ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    c->it_host = it;
+    c->labelled = false;
+    SrmCtl h;
+    return fetch_ctl(c, &h);
+}
+
 static void fill_stats(const SrmCtl &h, srm_stats *s, float ms) {
     if (!s) return;
     s->iterations = h.it; s->num_sites = h.K; s->stopped = h.stop; s->omega = h.omega; s->energy = h.E; s->ms_device = ms;
