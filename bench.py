@@ -177,6 +177,7 @@ def run_ours(args):
     if world == 1:
         stage = eng.ctx.iterate_profiled(K, stop_rule=False)
         torch.cuda.synchronize()
+        runs, ovf = eng.ctx.debug_counts()
 
     # ---- end to end through the reference-facing call, host buffers in pinned memory
     e2e_iters = args.e2e_iters
@@ -231,8 +232,8 @@ def run_ours(args):
         "config": {"workload": f"C3 curvature-like anisotropic density {n}x{n}, {k} sites + {int(mask.sum())} fixed boundary sites "
                                "(BASELINE.json configs[2])", "grid": n, "sites": st["num_sites"],
                    "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
-                   "l2": "per-step working set (column map 2 B/px + fp64 prefix arrays 24 B/px touched at run ends) "
-                         f"= {(2 * N + 24 * N) / 1e6:.0f} MB > 126 MB L2; no explicit flush",
+                   "l2": "fp64 prefix arrays (24 B/px, read at run ends) + site-id map (4 B/px, read per run) "
+                         f"= {28 * N / 1e6:.0f} MB > 126 MB L2; no explicit flush",
                    "stop_rule": "off (fixed step count); energy every 10th step like the reference"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "iterations_per_call": e2e_iters, "api": "gCVT(host buffers)" if world == 1 else "ShardedLloyd(host buffers)"},
@@ -240,11 +241,13 @@ def run_ours(args):
         "clocks": clocks,
     }
     if stage is not None:
-        row_ms = stage["row_envelope"] / K
-        runs_bytes = 8.0 * 2.6e6 * (N / 67108864.0)  # ~8 B per run written (measured ~2.6 M runs at 8192^2/100k)
-        alg = 2.0 * N + runs_bytes
+        row_ms = stage["band_fused"] / K
+        # algorithmic bytes of one k_band launch: per 16-row band and column 8 B (bitmap word + up/dn carries)
+        # = N/2; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
+        alg = 0.5 * N + 52.0 * runs
         ach = alg / (row_ms / 1e3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "k_row (row envelope: 2 B/px column map in, 8 B/run out)",
+        line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; N/2 B + 52 B/run)",
+                            "runs_per_step": runs, "robust_path_rows": ovf,
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                             "peak_source": peak_src, "ms_per_launch": row_ms,
                             "note": "integer/latency bound, not HBM bound: see DESIGN.md §roofline",

@@ -91,11 +91,15 @@ int srm_set_site_map(srm_ctx *ctx, const short *site_map, int on_device);
 int srm_set_sites(srm_ctx *ctx, const int *packed_xy, int num, int on_device);
 int srm_get_sites(srm_ctx *ctx, int *packed_xy_host, int capacity, int *num_out);
 int srm_set_omega(srm_ctx *ctx, float omega);
+/* Options: "robust_only" = 1 labels every row with the worst-case-capacity row path instead of the fused band
+ * kernel (same results; used by the tests to pin that path). */
+int srm_set_option(srm_ctx *ctx, const char *name, int value);
 
 /* Steps of one Lloyd iteration (gcvt.cu:1112-1123), all asynchronous on the context's stream. */
 int srm_label(srm_ctx *ctx);                       /* pba2DCompute: exact labels of the current sites (run-length form) */
 int srm_accumulate(srm_ctx *ctx, int want_energy); /* pbaCVDComputeCentroid (+pbaCVDCalcEnergy): per-site sums over this band */
 int srm_update(srm_ctx *ctx);                      /* pbaCVDUpdateSites + the control block of gcvt.cu:1123-1140 */
+int srm_label_accumulate(srm_ctx *ctx, int want_energy); /* srm_label + srm_accumulate fused in one kernel pass */
 /* Device accumulators for an external all-reduce between srm_accumulate and srm_update:
  * 4*capacity+4 doubles: (W, X, Y, 0) per site, then (energy_sum,0,0,0). */
 int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
@@ -104,11 +108,14 @@ int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */
 int srm_iterate(srm_ctx *ctx, int iters, int stop_rule);
 /* Same loop with CUDA events between the stages (measurement only): stage_ms[6] receives the summed device
- * milliseconds of {site bitmap + carries, column pass, row envelope, accumulate, update + control, whole iteration}. */
+ * milliseconds of {site bitmap + carries, fused band kernel, robust-path column + row, robust-path accumulate,
+ * update + control, whole iteration}. */
 int srm_iterate_profiled(srm_ctx *ctx, int iters, int stop_rule, float *stage_ms);
 /* Whole gCVT on resident inputs: loop + final labelling. */
 int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);
 int srm_get_state(srm_ctx *ctx, srm_stats *stats);
+/* Measurement helper: runs produced by the last labelling and rows that took the robust path. */
+int srm_debug_counts(srm_ctx *ctx, long long *total_runs, int *overflow_rows);
 
 /* Dense labels of this band (rows row0..row1): expands the run-length labels of the last srm_label.
  * out: (row1-row0)*n short2. */

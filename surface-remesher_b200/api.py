@@ -57,20 +57,23 @@ def lib():
     L.srm_set_sites.argtypes = [p, p, i, i]
     L.srm_get_sites.argtypes = [p, p, i, C.POINTER(i)]
     L.srm_set_omega.argtypes = [p, C.c_float]
+    L.srm_set_option.argtypes = [p, C.c_char_p, i]
     L.srm_label.argtypes = [p]
     L.srm_accumulate.argtypes = [p, i]
+    L.srm_label_accumulate.argtypes = [p, i]
     L.srm_update.argtypes = [p]
     L.srm_acc_buffer.argtypes = [p, C.POINTER(p), C.POINTER(C.c_size_t)]
     L.srm_iterate.argtypes = [p, i, i]
     L.srm_iterate_profiled.argtypes = [p, i, i, p]
     L.srm_run.argtypes = [p, i, i, p]
     L.srm_get_state.argtypes = [p, p]
+    L.srm_debug_counts.argtypes = [p, C.POINTER(C.c_longlong), C.POINTER(i)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
                  "srm_set_stream", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
-                 "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_label", "srm_accumulate", "srm_update",
-                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_get_labels", "srm_label_jfa"):
+                 "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
+                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -231,6 +234,9 @@ class Context:
         _ck(lib().srm_get_sites(self._h, out.ctypes.data_as(C.c_void_p), k.value, C.byref(k)))
         return out[: k.value]
 
+    def set_option(self, name, value):
+        _ck(lib().srm_set_option(self._h, name.encode(), int(value)))
+
     def set_omega(self, omega):
         _ck(lib().srm_set_omega(self._h, float(omega)))
 
@@ -239,6 +245,9 @@ class Context:
 
     def accumulate(self, want_energy):
         _ck(lib().srm_accumulate(self._h, int(bool(want_energy))))
+
+    def label_accumulate(self, want_energy):
+        _ck(lib().srm_label_accumulate(self._h, int(bool(want_energy))))
 
     def update(self):
         _ck(lib().srm_update(self._h))
@@ -252,7 +261,7 @@ class Context:
     def iterate(self, iters, stop_rule=False):
         _ck(lib().srm_iterate(self._h, int(iters), int(bool(stop_rule))))
 
-    STAGES = ("bitmap+carry", "column", "row_envelope", "accumulate", "update", "iteration")
+    STAGES = ("bitmap+carry", "band_fused", "robust_col_row", "robust_accumulate", "update", "iteration")
 
     def iterate_profiled(self, iters, stop_rule=False):
         """dict stage -> summed device ms over `iters` iterations (CUDA events between the stages)."""
@@ -269,6 +278,12 @@ class Context:
         st = Stats()
         _ck(lib().srm_get_state(self._h, C.byref(st)))
         return st.as_dict()
+
+    def debug_counts(self):
+        """(total runs of the last labelling, rows that took the robust path)."""
+        runs, ovf = C.c_longlong(), C.c_int()
+        _ck(lib().srm_debug_counts(self._h, C.byref(runs), C.byref(ovf)))
+        return runs.value, ovf.value
 
     def get_labels(self, out=None):
         rows = self.row1 - self.row0

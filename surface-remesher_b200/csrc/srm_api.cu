@@ -13,6 +13,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <algorithm>
 #include <vector>
 
@@ -60,6 +61,9 @@ struct srm_ctx {
     short *up = nullptr, *dn = nullptr, *cy = nullptr;
     int2 *rle = nullptr;
     int *rle_cnt = nullptr, *idmap = nullptr, *claim = nullptr, *labels = nullptr, *scratch_map = nullptr;
+    int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
+    int dbg_stats = 0;
+    bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
     SrmCtl *ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
@@ -106,6 +110,13 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
         return fail(SRM_ERR_CUDA, "srm_create: no CUDA device (libsrm has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(SRM_ERR_ARG, "srm_create: device %d of %d", device, ndev);
     CK(cudaSetDevice(device));
+    {   // The accumulate pass reads one 16-byte fp64 prefix pair per run end, scattered over a >1 GB array: with the
+        // default 128-byte L2 fetch granularity every lookup costs a full line of DRAM traffic (measured 621 MB
+        // per launch at 8192^2, ncu).  32-byte granularity fetches the one sector that is needed.
+        const char *env = getenv("SRM_L2_FETCH");
+        size_t gran = env ? (size_t)atoi(env) : 32;
+        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+    }
     srm_ctx *c = new srm_ctx();
     c->g.n = n; c->g.row0 = row0; c->g.row1 = row1;
     c->device = device;
@@ -134,6 +145,7 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->cy, NB * sizeof(short)));
     CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
+    CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->idmap, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->claim, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
@@ -155,7 +167,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
-                    c->blockoff, c->bits, c->up, c->dn, c->cy, c->rle, c->rle_cnt, c->idmap, c->claim, c->labels,
+                    c->blockoff, c->bits, c->up, c->dn, c->cy, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
                     c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -272,6 +284,39 @@ extern "C" int srm_get_sites(srm_ctx *c, int *packed_xy_host, int capacity, int 
     return SRM_OK;
 }
 
+// Measurement helper: total number of runs of the last labelling and rows that took the robust path.
+extern "C" int srm_debug_counts(srm_ctx *c, long long *total_runs, int *overflow_rows) {
+    if (!c || !total_runs || !overflow_rows) return fail(SRM_ERR_ARG, "srm_debug_counts: null argument");
+    CK(cudaSetDevice(c->device));
+    std::vector<int> h((size_t)c->g.nrows());
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(h.data(), c->rle_cnt, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    long long tot = 0;
+    for (int v : h) tot += v;
+    *total_runs = tot;
+    SrmCtl hc;
+    CK(cudaMemcpy(&hc, c->ctl, sizeof(hc), cudaMemcpyDeviceToHost));
+    *overflow_rows = c->robust_only ? c->g.nrows() : hc.ovf;
+    if (c->dbg_stats)
+        fprintf(stderr, "[srm dbg] band list: max %d mean %.1f (%d bands) | row survivors: max %d mean %.1f (%d rows)\n",
+                hc.dbg[0], hc.dbg[2] ? (double)hc.dbg[1] / hc.dbg[2] : 0.0, hc.dbg[2], hc.dbg[3],
+                hc.dbg[5] ? (double)hc.dbg[4] / hc.dbg[5] : 0.0, hc.dbg[5]);
+    return SRM_OK;
+}
+
+// Options: "robust_only" (0/1): label with the worst-case-capacity row path only (no fused band kernel).
+extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
+    if (!c || !name) return fail(SRM_ERR_ARG, "srm_set_option: null argument");
+    if (!strcmp(name, "robust_only")) { c->robust_only = value != 0; return SRM_OK; }
+    if (!strcmp(name, "dbg_stats")) {
+        c->dbg_stats = value;
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemset(c->ctl->dbg, 0, sizeof(c->ctl->dbg)));
+        return SRM_OK;
+    }
+    return fail(SRM_ERR_ARG, "srm_set_option: unknown option %s", name);
+}
+
 extern "C" int srm_set_omega(srm_ctx *c, float omega) {
     if (!c) return fail(SRM_ERR_ARG, "null ctx");
     CK(cudaSetDevice(c->device));
@@ -284,11 +329,22 @@ extern "C" int srm_set_omega(srm_ctx *c, float omega) {
 // Inside the loop both agree until a stop; after a stop every kernel is a no-op, so using the
 // host parity for the (skipped) launches is harmless.  For calls outside the loop (final labelling)
 // the parity is read back from the device.
-static int label_with(srm_ctx *c, int buf, int respect_stop) {
+static int label_with(srm_ctx *c, int buf, int respect_stop, int accumulate, int want_energy) {
     srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop);
     srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop);
-    srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, c->ctl, respect_stop);
-    CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, c->ctl, respect_stop));
+    const int *rows = nullptr, *count = nullptr;
+    if (!c->robust_only) {
+        CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+                           c->idmap, c->acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, c->dbg_stats));
+        rows = c->ovf_rows;
+        count = &c->ctl->ovf;
+    }
+    srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, rows, count, c->ctl, respect_stop);
+    CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, rows, count, c->ctl, respect_stop));
+    if (accumulate)
+        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, rows, count, c->ctl,
+                       want_energy, respect_stop);
+    CK(cudaGetLastError());
     return SRM_OK;
 }
 
@@ -303,7 +359,19 @@ extern "C" int srm_label(srm_ctx *c) {
     int rc = require_ready(c, "srm_label", false);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
-    rc = label_with(c, current_buffer(c), 0);
+    rc = label_with(c, current_buffer(c), 0, 0, 0);
+    if (rc) return rc;
+    c->labelled = true;
+    return SRM_OK;
+}
+
+// Fused stepwise variant: labelling and per-site accumulation in one pass of the band kernel (what
+// srm_iterate does per iteration), for callers that all-reduce the accumulators before srm_update.
+extern "C" int srm_label_accumulate(srm_ctx *c, int want_energy) {
+    int rc = require_ready(c, "srm_label_accumulate", true);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    rc = label_with(c, current_buffer(c), 0, 1, want_energy);
     if (rc) return rc;
     c->labelled = true;
     return SRM_OK;
@@ -314,7 +382,8 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     if (rc) return rc;
     if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
     CK(cudaSetDevice(c->device));
-    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl, want_energy, 0);
+    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, nullptr, nullptr, c->ctl,
+                   want_energy, 0);
     CK(cudaGetLastError());
     return SRM_OK;
 }
@@ -352,10 +421,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     int it = c->it_host;
     for (int i = 0; i < iters; ++i, ++it) {
         const int buf = it & 1, want_energy = (it % 10) == 0;
-        rc = label_with(c, buf, 1);
+        rc = label_with(c, buf, 1, 1, want_energy);
         if (rc) return rc;
-        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl,
-                       want_energy, 1);
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
                           c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt,
                           c->blockoff, want_energy, stop_rule, 1);
@@ -372,7 +439,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
 }
 
 // Same loop as srm_iterate with CUDA events between the stages; stage_ms[6] receives the summed device
-// time of {site bitmap+carry, column pass, row envelope, accumulate, update+control, whole iteration}.
+// time of {site bitmap + carries, fused band kernel, robust-path column+row, robust-path accumulate,
+// update + control, whole iteration}.
 extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float *stage_ms) {
     int rc = require_ready(c, "srm_iterate_profiled", true);
     if (rc) return rc;
@@ -390,11 +458,18 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1);
         srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1);
         CK(cudaEventRecord(e[1], c->stream));
-        srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, c->ctl, 1);
+        const int *rows = nullptr, *count = nullptr;
+        if (!c->robust_only) {
+            CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+                               c->idmap, c->acc, c->Kcap, c->ctl, 1, want_energy, 1, c->dbg_stats));
+            rows = c->ovf_rows;
+            count = &c->ctl->ovf;
+        }
         CK(cudaEventRecord(e[2], c->stream));
-        CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, c->ctl, 1));
+        srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, rows, count, c->ctl, 1);
+        CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, rows, count, c->ctl, 1));
         CK(cudaEventRecord(e[3], c->stream));
-        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, c->ctl,
+        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, rows, count, c->ctl,
                        want_energy, 1);
         CK(cudaEventRecord(e[4], c->stream));
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
@@ -505,15 +580,27 @@ extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned cha
     (void)depth;  // single level; see DESIGN.md (gcvt.h cannot drive depth > 1 either)
     int dev = 0;
     cudaGetDevice(&dev);
+    const bool trace = getenv("SRM_TRACE") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    double t0 = now(), t1;
+#define TR(what) do { if (trace) { t1 = now(); fprintf(stderr, "[srm_gcvt] %-12s %8.2f ms\n", what, t1 - t0); t0 = t1; } } while (0)
     srm_ctx *c = nullptr;
     int rc = srm_create(&c, n, 0, n, dev);
     if (rc) return rc;
+    TR("create");
     rc = srm_set_density(c, density, 0);
+    TR("density");
     if (!rc) rc = srm_set_mask(c, mask, 0);
+    TR("mask");
     if (!rc) rc = srm_set_site_map(c, voronoi, 0);
+    TR("site_map");
     if (!rc) rc = srm_run(c, max_iter, 1, stats);
+    TR("run");
     if (!rc) rc = srm_get_labels(c, voronoi, 0);
+    TR("get_labels");
     srm_destroy(c);
+    TR("destroy");
+#undef TR
     return rc;
 }
 

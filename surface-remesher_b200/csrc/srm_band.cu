@@ -1,0 +1,351 @@
+// srm_band.cu — fused band kernel: exact labelling of R = 16 consecutive rows straight from the
+// column bitmap, run-length output and (optionally) the per-site centroid/energy accumulation, in
+// one launch.  This is the hot kernel of the Lloyd loop; it replaces the reference's pba2DCompute +
+// pbaCVDComputeCentroid (+ pbaCVDCalcEnergy) chain (gcvt.cu:921-978, 1008-1023, 1059-1083: ~15
+// launches, ~75 B/px) and never materialises a per-pixel array.
+//
+// One CTA = 8 warps = one band of R = 8*RPW rows.
+//   Phase A (whole CTA, once per band): per column, from the bitmap word and the up/dn carries, the
+//     nearest site row above the band (U), below it (D) and the in-band bits.  Columns that are
+//     dominated for EVERY row of the band by both neighbouring 8-column blocks are dropped
+//     (bounds: gmin = min over the band of |dy|, gmax <= gmin + R - 1); survivors are compacted
+//     into the band list (x, U, D, inband bits) in shared memory, ordered by x.
+//   Phase B (one warp per row): the row's lower envelope by DOMINANCE ROUNDS.  Element e of the current
+//     list wins on the integer interval (B(e-1,e), B(e,e+1)]; if that interval is empty (or beyond the
+//     grid) e is dropped.  All elements of a round are tested in parallel against the round's input
+//     list (sound with stale neighbours), survivors are compacted in place in a 4 KB per-warp buffer,
+//     and rounds repeat until nothing is dropped.  Round 0 reads the band list (row candidate c(x,Y) by
+//     the tie rule of A2).  On Voronoi-like data the list shrinks ~3x per round (measured 1654 -> 554 ->
+//     187 -> 95 -> 76 -> 70 -> 69; total work 1.9x the band list), every instruction runs on 32 lanes,
+//     and there are no stacks, no merges, no capacities other than "envelope <= 993 elements per row".
+//     The output pass writes the runs and, in accumulate mode, adds the fp64 prefix differences of each
+//     run to its site's accumulators (centroid + energy).
+// A band whose list exceeds CL entries, or a row whose envelope exceeds the buffer, is handed to the
+// robust path (k_col/k_row/k_acc).
+#include "srm_common.cuh"
+#include "srm_envelope.cuh"
+
+#define BAND_NT 256
+#define BAND_NW 8
+
+struct Col8 {          // 8 consecutive columns of one band
+    int U[8], D[8];    // nearest site row above / below the band (SRM_MARK if none)
+    uint32_t inb[8];   // site bits inside the band, bit k = row Y0 + k
+    int gmin[8];       // lower bound of |dy| over the band's rows (SRM_BIG: no site in the column)
+    int M;             // min over the 8 columns of the upper bound gmax
+};
+
+template <int R>
+__device__ __forceinline__ void load_col8(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                          const short *__restrict__ dn, size_t o, int j, int k0, int Y0, Col8 &c) {
+    const uint4 w0 = *reinterpret_cast<const uint4 *>(bits + o), w1 = *reinterpret_cast<const uint4 *>(bits + o + 4);
+    const uint4 u4 = *reinterpret_cast<const uint4 *>(up + o), d4 = *reinterpret_cast<const uint4 *>(dn + o);
+    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+    const uint32_t rmask = (R == 32) ? 0xffffffffu : ((1u << R) - 1u);
+    c.M = SRM_BIG;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int u0 = (short)((uu[k >> 1] >> ((k & 1) * 16)) & 0xffff), d0 = (short)((dd[k >> 1] >> ((k & 1) * 16)) & 0xffff);
+        const uint32_t lo = k0 ? (w[k] & ((1u << k0) - 1u)) : 0u;
+        const uint32_t hi = (k0 + R < 32) ? (w[k] >> (k0 + R)) : 0u;
+        const uint32_t in = (w[k] >> k0) & rmask;
+        const int U = lo ? 32 * j + 31 - __clz(lo) : u0;
+        const int D = hi ? Y0 + R + __ffs(hi) - 1 : d0;
+        int gmin, gmax;
+        if (in) { gmin = 0; gmax = R - 1; }
+        else {
+            const int gu = (U == SRM_MARK) ? SRM_BIG : Y0 - U, gd = (D == SRM_MARK) ? SRM_BIG : D - (Y0 + R - 1);
+            gmin = min(gu, gd);
+            gmax = (gmin == SRM_BIG) ? SRM_BIG : gmin + R - 1;
+        }
+        c.U[k] = U; c.D[k] = D; c.inb[k] = in; c.gmin[k] = gmin;
+        c.M = min(c.M, gmax);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ int block_gmax(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                          const short *__restrict__ dn, size_t o, int j, int k0, int Y0) {
+    Col8 c;
+    load_col8<R>(bits, up, dn, o, j, k0, Y0, c);
+    return c.M;
+}
+
+template <int R>
+__device__ __forceinline__ unsigned live_mask(const Col8 &c, int ML, int MR) {
+    const int TL = ML * ML + 225, TR = MR * MR + 225;  // 15 = farthest column of an adjacent 8-block
+    unsigned live = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int g2 = c.gmin[k] * c.gmin[k];
+        const bool dead = (c.gmin[k] == SRM_BIG) || (g2 >= TL && g2 > TR);
+        live |= dead ? 0u : (1u << k);
+    }
+    return live;
+}
+
+// Row candidate of a band-list entry for row Y = Y0 + k (Appendix A2 column rule).
+__device__ __forceinline__ int row_candidate(int U, int D, uint32_t inb, int Y0, int k, int Y) {
+    if (inb) {
+        const uint32_t lo = inb & (0xffffffffu >> (31 - k));
+        const uint32_t hi = (k == 31) ? 0u : (inb & (0xffffffffu << (k + 1)));
+        if (lo) U = Y0 + 31 - __clz(lo);
+        if (hi) D = Y0 + __ffs(hi) - 1;
+    }
+    return srm_choose_col(U, D, Y);
+}
+
+// floor(num/den) for 0 <= num < (n-1)*den, den in [2, 65534]: approximate float quotient (|error| <= 1) + fix-up
+__device__ __forceinline__ int floordiv_pos(int num, int den) {
+    int q = __float2int_rz(__fdividef(__int2float_rz(num), __int2float_rn(den)));
+    const int r = num - q * den;
+    if (r < 0) --q;
+    else if (r >= den) ++q;
+    return q;
+}
+
+// Integer breakpoint between neighbours p < q of a row: p wins (ties included, smallest x first, reference
+// kernelColor gcvt.cu:449-466) exactly for X <= B = floor((H_q - H_p) / (2 (x_q - x_p))), clamped to [-1, n-1].
+__device__ __forceinline__ int breakpoint(int num, int den, int n) {
+    if (num < 0) return -1;
+    if (num >= (n - 1) * den) return n - 1;
+    return floordiv_pos(num, den);
+}
+
+// Candidate of band-list entry i for row Y = Y0 + k: packed x | c << 16 and H = x^2 + (c - Y)^2.
+__device__ __forceinline__ void load_cand(const uint2 *__restrict__ L, int i, int Y0, int k, int Y, unsigned &v, int &x,
+                                          int &H) {
+    const uint2 e = L[i];
+    x = (int)(e.x & 0xffffu);
+    const int c = row_candidate((int)(short)(e.y & 0xffffu), (int)e.y >> 16, e.x >> 16, Y0, k, Y);
+    const int g = c - Y;
+    v = (unsigned)x | ((unsigned)c << 16);
+    H = x * x + g * g;
+}
+
+// One step of a dominance round over 31 consecutive elements (lane 31 is a read-only lookahead).
+// Element e wins on the integer interval (Bc, B]: B = breakpoint with its successor, Bc = breakpoint with its
+// predecessor (carry across steps).  It is dropped when that interval is empty or lies beyond the grid; dropping
+// is sound with stale neighbours (a pair that beats e everywhere exists either way), so all elements of a round
+// are tested against the round's input list, in parallel.
+struct RoundStep {
+    int B, Bc;
+    bool owned, keep;
+};
+__device__ __forceinline__ RoundStep round_step(bool valid, int x, int H, int lane, int n, int &carryB) {
+    RoundStep r;
+    const int xn = __shfl_down_sync(0xffffffffu, x, 1), Hn = __shfl_down_sync(0xffffffffu, H, 1);
+    const bool validn = __shfl_down_sync(0xffffffffu, (int)valid, 1) != 0;
+    r.owned = valid && lane < 31;
+    r.B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
+    r.Bc = __shfl_up_sync(0xffffffffu, r.B, 1);
+    if (lane == 0) r.Bc = carryB;
+    carryB = __shfl_sync(0xffffffffu, r.B, 30);
+    r.keep = r.owned && r.B > r.Bc && r.Bc < n - 1;
+    return r;
+}
+
+template <int RPW, int C>
+__global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                                  const short *__restrict__ dn, int n, int row0, int CL,
+                                                  int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
+                                                  const double2 *__restrict__ P2, const double *__restrict__ PXX,
+                                                  const int *__restrict__ idmap, double *__restrict__ acc, int Kcap,
+                                                  SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
+                                                  int dbg) {
+    constexpr int R = BAND_NW * RPW;
+    static_assert(R <= 16, "in-band bits are packed in 16 bits");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int wcnt[BAND_NW];
+    if (respect_stop && ctl->stop) return;
+
+    uint2 *L = reinterpret_cast<uint2 *>(smem_raw);                       // band list: {x | inband << 16, U | D << 16}
+    unsigned char *masks = reinterpret_cast<unsigned char *>(L + CL);      // live mask per 8-column block
+    unsigned *buf0 = reinterpret_cast<unsigned *>(masks + ((n / 8 + 15) & ~15));  // per-warp element buffers
+
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int rb = blockIdx.x * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
+    const size_t wrow = (size_t)j * n;
+    const int nb = n >> 3;
+    const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
+
+    // ---- Phase A, pass 1: live mask of every 8-column block (30 owned blocks per step + one halo block each side)
+    int mycount = 0;
+    for (int b0 = bw0; b0 < bw1; b0 += 30) {
+        const int b = b0 - 1 + lane;
+        Col8 col;
+        col.M = SRM_BIG;
+        if (b >= 0 && b < nb) load_col8<R>(bits, up, dn, wrow + (size_t)b * 8, j, k0, Y0, col);
+        const int ML = __shfl_up_sync(0xffffffffu, col.M, 1), MR = __shfl_down_sync(0xffffffffu, col.M, 1);
+        if (lane >= 1 && lane <= 30 && b < bw1) {
+            const unsigned live = live_mask<R>(col, ML, MR);
+            masks[b] = (unsigned char)live;
+            mycount += __popc(live);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) mycount += __shfl_xor_sync(0xffffffffu, mycount, o);
+    if (lane == 0) wcnt[w] = mycount;
+    __syncthreads();
+    int mb = 0, wbase = 0;
+#pragma unroll
+    for (int k = 0; k < BAND_NW; ++k) { if (k < w) wbase += wcnt[k]; mb += wcnt[k]; }
+    if ((dbg & 1) && t == 0) { atomicMax(&ctl->dbg[0], mb); atomicAdd(&ctl->dbg[1], mb); atomicAdd(&ctl->dbg[2], 1); }
+    if (mb > CL) {  // band list does not fit: every row of the band goes to the robust path
+        if (t < R) ovf_rows[atomicAdd(&ctl->ovf, 1)] = rb + t;
+        return;
+    }
+    // ---- Phase A, pass 2: write the band list in column order
+    {
+        int base = wbase;
+        for (int b0 = bw0; b0 < bw1; b0 += 32) {
+            const int b = b0 + lane;
+            const unsigned live = (b < bw1) ? masks[b] : 0u;
+            const int cnt = __popc(live);
+            const int incl = warp_incl_scan(cnt, lane);
+            if (live) {
+                Col8 col;
+                load_col8<R>(bits, up, dn, wrow + (size_t)b * 8, j, k0, Y0, col);
+                int o = base + incl - cnt;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (live & (1u << k)) {
+                        L[o] = make_uint2((unsigned)(b * 8 + k) | (col.inb[k] << 16),
+                                          ((unsigned)col.U[k] & 0xffffu) | ((unsigned)col.D[k] << 16));
+                        ++o;
+                    }
+            }
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    __syncthreads();
+
+    // ---- Phase B: warp w computes the envelopes of rows rb + w*RPW .. +RPW-1 by dominance rounds
+    unsigned *buf = buf0 + (size_t)w * C;
+    const unsigned lt = (1u << lane) - 1u;
+    double e_loc = 0;
+    for (int rr = 0; rr < RPW; ++rr) {
+        const int k = w * RPW + rr, r = rb + k, Y = Y0 + k;
+        int m = 0, pos = 0, carry0 = -1;
+        bool overflow = false;
+        for (;;) {
+            // round 0: candidates of the band list, tested against their list neighbours, appended to buf
+            while (pos < mb && m + 31 <= C) {
+                const int e = pos + lane;
+                const bool valid = e < mb;
+                unsigned v = 0;
+                int x = 0, H = 0;
+                if (valid) load_cand(L, e, Y0, k, Y, v, x, H);
+                const RoundStep st = round_step(valid, x, H, lane, n, carry0);
+                const unsigned bal = __ballot_sync(0xffffffffu, st.keep);
+                if (st.keep) buf[m + __popc(bal & lt)] = v;
+                m += __popc(bal);
+                pos += 31;
+            }
+            __syncwarp();
+            // rounds over buf until nothing is dropped
+            for (;;) {
+                int wp = 0, carryB = -1, total_owned = 0;
+                for (int base = 0; base < m; base += 31) {
+                    const int e = base + lane;
+                    const bool valid = e < m;
+                    const unsigned v = valid ? buf[e] : 0u;
+                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y, H = x * x + g * g;
+                    const RoundStep st = round_step(valid, x, H, lane, n, carryB);
+                    const unsigned bal = __ballot_sync(0xffffffffu, st.keep);
+                    __syncwarp();
+                    if (st.keep) buf[wp + __popc(bal & lt)] = v;
+                    wp += __popc(bal);
+                    total_owned += min(31, m - base);
+                }
+                __syncwarp();
+                const bool removed = wp != m;
+                m = wp;
+                if (!removed) break;
+                (void)total_owned;
+            }
+            if (pos >= mb) break;
+            if (m + 31 > C) { overflow = true; break; }  // the envelope itself does not fit
+        }
+        if (overflow) {
+            if (lane == 0) ovf_rows[atomicAdd(&ctl->ovf, 1)] = r;
+            continue;
+        }
+        // output pass: runs -> global run-length row, and (accumulate mode) fp64 prefix differences -> site sums
+        int2 *out = rle + (size_t)r * n;
+        const double2 *p2 = P2 + (size_t)r * n;
+        const double *pxx = PXX + (size_t)r * n;
+        int carryB = -1;
+        double2 carryP = make_double2(0, 0);
+        double carryXX = 0;
+        for (int base = 0; base < m; base += 31) {
+            const int e = base + lane;
+            const bool valid = e < m;
+            const unsigned v = valid ? buf[e] : 0u;
+            const int x = (int)(v & 0xffffu), c = (int)(v >> 16), g = c - Y, H = x * x + g * g;
+            const RoundStep st = round_step(valid, x, H, lane, n, carryB);
+            if (st.owned) out[e] = make_int2((int)v, st.Bc + 1);
+            if (accumulate) {
+                double2 pb = (st.owned && !(dbg & 8)) ? p2[st.B] : make_double2(1, 1);
+                double xb = (st.owned && want_energy) ? pxx[st.B] : 0;
+                double2 pa;
+                pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1);
+                pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);
+                double xa = __shfl_up_sync(0xffffffffu, xb, 1);
+                if (lane == 0) { pa = carryP; xa = carryXX; }
+                carryP.x = __shfl_sync(0xffffffffu, pb.x, 30);
+                carryP.y = __shfl_sync(0xffffffffu, pb.y, 30);
+                carryXX = __shfl_sync(0xffffffffu, xb, 30);
+                if (st.owned) {
+                    const double W = pb.x - pa.x, X = pb.y - pa.y;
+                    const int id = (dbg & 4) ? (e + 37 * r) % Kcap : idmap[(size_t)c * n + x];
+                    double *a = acc + 4 * (size_t)id;
+                    if (!(dbg & 2)) {
+                        atomicAdd(a, W);
+                        atomicAdd(a + 1, X);
+                        atomicAdd(a + 2, (double)Y * W);
+                    } else if (W == -1.5) a[3] = X;
+                    if (want_energy) e_loc += (xb - xa) - 2.0 * (double)x * X + (double)(H) * W;
+                }
+            }
+        }
+        if (lane == 0) rle_cnt[r] = m;
+        __syncwarp();
+    }
+    if (accumulate && want_energy) {
+        e_loc = warp_sum(e_loc);
+        if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
+    }
+}
+
+#define BAND_RPW 2
+#define BAND_C 1024
+
+static int band_cap(int n) {
+    // measured on C3-like inputs (DESIGN.md §band kernel): band list <= ~0.28 n
+    int cl = (3 * n) / 8;
+    if (cl > 2816) cl = 2816;  // 4 CTAs/SM: 4 x (22 KB list + 1 KB masks + 32 KB element buffers + static/system)
+    if (cl < 512) cl = 512;
+    return cl;
+}
+
+static size_t band_smem(int n, int CL) {
+    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * BAND_C * 4;
+}
+
+cudaError_t srm_band_setup(int n) {
+    return cudaFuncSetAttribute(k_band<BAND_RPW, BAND_C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)band_smem(n, band_cap(n)));
+}
+
+cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
+                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
+                            double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
+                            int dbg) {
+    const int CL = band_cap(g.n);
+    const int R = BAND_NW * BAND_RPW;
+    k_band<BAND_RPW, BAND_C><<<g.nrows() / R, BAND_NT, band_smem(g.n, CL), st>>>(
+        bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
+        respect_stop, dbg);
+    return cudaGetLastError();
+}

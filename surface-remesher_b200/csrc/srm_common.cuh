@@ -18,7 +18,8 @@ struct SrmCtl {
     float omega;    // pbaOmega
     float lastE;    // lastEnergy
     float E;        // Energy (float like the reference)
-    int pad;
+    int ovf;        // rows handed to the robust path by the band kernel (this labelling)
+    int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
 };
 
 __host__ __device__ __forceinline__ int srm_pack(int x, int y) { return (x & 0xffff) | (y << 16); }
@@ -57,21 +58,28 @@ struct SrmGrid {           // geometry of one context
     int nrows() const { return row1 - row0; }
 };
 
-void srm_launch_bits(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
+void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
                      int *claim, int respect_stop);
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
                       int respect_stop);
+// fused fast path (srm_band.cu)
+cudaError_t srm_band_setup(int n);
+cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
+                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
+                            double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
+                            int dbg = 0);
+// robust path, driven by a row list (rows == nullptr: every row of the band)
 void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
-                    const SrmCtl *ctl, int respect_stop);
-cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const SrmCtl *ctl,
-                           int respect_stop);
+                    const int *rows, const int *count, const SrmCtl *ctl, int respect_stop);
+cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const int *rows,
+                           const int *count, const SrmCtl *ctl, int respect_stop);
 cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels);
 cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes
 
 void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX);
 void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
-                    const int *idmap, SrmGrid g, double *acc, int Kcap, const SrmCtl *ctl, int want_energy,
-                    int respect_stop);
+                    const int *idmap, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
+                    const SrmCtl *ctl, int want_energy, int respect_stop);
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
                        const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int *blockcnt,
                        int *blockoff, int want_energy, int stop_rule, int respect_stop);

@@ -14,12 +14,14 @@
 // All arithmetic is integer; ties follow the reference (column tie: gcvt.cu:97-119 + :172-216;
 // row tie -> smallest x: gcvt.cu:449-466).
 #include "srm_common.cuh"
+#include "srm_envelope.cuh"
 
 // ------------------------------------------------------------------ sites -> bitmap
 
-__global__ void k_bits(const int *__restrict__ sites, const SrmCtl *__restrict__ ctl, int n, uint32_t *bits,
-                       int *idmap, int *claim, int respect_stop) {
+__global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32_t *bits, int *idmap, int *claim,
+                       int respect_stop) {
     if (respect_stop && ctl->stop) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ovf = 0;  // rows the band kernel hands to the robust path
     int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     int p = sites[id];
@@ -30,12 +32,12 @@ __global__ void k_bits(const int *__restrict__ sites, const SrmCtl *__restrict__
     claim[i] = INT_MAX; // reset the dedupe claim left by the previous update
 }
 
-void srm_launch_bits(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
+void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
                      int *claim, int respect_stop) {
     // the memset is skipped after a stop only in effect (bits are then unused until the final labelling
     // rebuilds them), so it can stay unconditional
     cudaMemsetAsync(bits, 0, (size_t)(n >> 5) * n * sizeof(uint32_t), st);
-    if (Kcap > 0) k_bits<<<(Kcap + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop);
+    k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop);
 }
 
 // Per column: up[j][x] = largest site row < 32j, dn[j][x] = smallest site row >= 32(j+1) (MARK if none).
@@ -74,45 +76,41 @@ void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, s
     k_carry<<<grid, 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop);
 }
 
-// cy[Y - row0][x] for the 32 rows of word-row j.
+// ------------------------------------------------------------------ robust row path (fallback)
+//
+// k_col + k_row handle ANY row with worst-case capacity (every column live): cy row -> prune ->
+// 128 thread stacks -> 7 bridging levels -> runs.  The fused band kernel (srm_band.cu) is the fast
+// path; rows whose candidate lists overflow its shared-memory budget are appended to a row list and
+// processed here.  rows == nullptr means "all rows of the band" (used by tests to pin this path).
+
+// cy[r][x] for the listed rows.
 __global__ void k_col(const uint32_t *__restrict__ bits, const short *__restrict__ up, const short *__restrict__ dn,
-                      int n, int row0, short *__restrict__ cy, const SrmCtl *__restrict__ ctl, int respect_stop) {
+                      int n, int row0, int nrows, short *__restrict__ cy, const int *__restrict__ rows,
+                      const int *__restrict__ count, const SrmCtl *__restrict__ ctl, int respect_stop) {
     if (respect_stop && ctl->stop) return;
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int j = blockIdx.y + (row0 >> 5);
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    size_t o = (size_t)j * n + x;
-    uint32_t w = bits[o];
-    int U0 = up[o], D0 = dn[o];
-    short *out = cy + (size_t)(32 * j - row0) * n + x;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        int Y = 32 * j + k;
-        uint32_t mlo = w & (0xffffffffu >> (31 - k));
-        uint32_t mhi = (k == 31) ? 0u : (w & (0xffffffffu << (k + 1)));
-        int U = mlo ? 32 * j + 31 - __clz(mlo) : U0;
-        int D = mhi ? 32 * j + __ffs(mhi) - 1 : D0;
-        out[(size_t)k * n] = (short)srm_choose_col(U, D, Y);
+    const int total = rows ? *count : nrows;
+    for (int q = blockIdx.y; q < total; q += gridDim.y) {
+        const int r = rows ? rows[q] : q, Y = row0 + r, j = Y >> 5, k = Y & 31;
+        const size_t o = (size_t)j * n + x;
+        const uint32_t w = bits[o];
+        const uint32_t mlo = w & (0xffffffffu >> (31 - k));
+        const uint32_t mhi = (k == 31) ? 0u : (w & (0xffffffffu << (k + 1)));
+        const int U = mlo ? 32 * j + 31 - __clz(mlo) : (int)up[o];
+        const int D = mhi ? 32 * j + __ffs(mhi) - 1 : (int)dn[o];
+        cy[(size_t)r * n + x] = (short)srm_choose_col(U, D, Y);
     }
 }
 
 void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
-                    const SrmCtl *ctl, int respect_stop) {
-    dim3 grid((g.n + 127) / 128, g.nrows() >> 5);
-    k_col<<<grid, 128, 0, st>>>(bits, up, dn, g.n, g.row0, cy, ctl, respect_stop);
+                    const int *rows, const int *count, const SrmCtl *ctl, int respect_stop) {
+    dim3 grid((g.n + 127) / 128, rows ? 16 : min(g.nrows(), 2048));
+    k_col<<<grid, 128, 0, st>>>(bits, up, dn, g.n, g.row0, g.nrows(), cy, rows, count, ctl, respect_stop);
 }
-
-// ------------------------------------------------------------------ row envelope
 
 #define ROW_NT 128
 #define ROW_NW (ROW_NT / 32)
-
-struct RowSmem {
-    unsigned short *lx;  // candidate column
-    short *lc;           // its site row c(x,Y)
-    short *lS;           // element wins for X > lS (within its merged group); -1 at the bottom
-    unsigned short *sb, *se;  // per-thread segment [sb,se)
-};
 
 __device__ __forceinline__ int min8_dist(uint4 v, int Y, int *g, short *cs) {
     uint32_t wv[4] = {v.x, v.y, v.z, v.w};
@@ -127,161 +125,97 @@ __device__ __forceinline__ int min8_dist(uint4 v, int Y, int *g, short *cs) {
     return M;
 }
 
-// Bridge two envelopes: segments [g0,gm) hold the left group, [gm,g1) the right group.
-// Pops dominated elements from the top of L and the bottom of R (PBA's band merge, gcvt.cu:293-410,
-// restated over integer breakpoints and contiguous smem segments).
-__device__ void merge_groups(const RowSmem &s, int g0, int gm, int g1, int Y, int n) {
-    int sl = gm - 1;
-    while (sl >= g0 && s.sb[sl] == s.se[sl]) --sl;
-    int sr = gm;
-    while (sr < g1 && s.sb[sr] == s.se[sr]) ++sr;
-    if (sl < g0 || sr >= g1) return;
-    int l = s.se[sl] - 1, r = s.sb[sr];
-    for (;;) {
-        int xl = s.lx[l], xr = s.lx[r];
-        int gl = s.lc[l] - Y, gr = s.lc[r] - Y;
-        int num = (xr * xr + gr * gr) - (xl * xl + gl * gl);
-        int den = 2 * (xr - xl);
-        if (num < ((int)s.lS[l] + 1) * den) {  // floor(num/den) <= S_l : l wins nowhere
-            s.se[sl] = (unsigned short)l;
-            if (l == s.sb[sl]) {
-                do { --sl; } while (sl >= g0 && s.sb[sl] == s.se[sl]);
-                if (sl < g0) { s.lS[r] = -1; return; }
-            }
-            l = s.se[sl] - 1;
-            continue;
-        }
-        bool rdead = num >= (n - 1) * den;  // r beats l only beyond the grid
-        if (!rdead) {
-            int r2 = -1;
-            if (r + 1 < s.se[sr]) r2 = r + 1;
-            else {
-                int s2 = sr + 1;
-                while (s2 < g1 && s.sb[s2] == s.se[s2]) ++s2;
-                if (s2 < g1) r2 = s.sb[s2];
-            }
-            if (r2 >= 0 && num >= (int)s.lS[r2] * den) rdead = true;  // floor(num/den) >= S_r2
-        }
-        if (rdead) {
-            s.sb[sr] = (unsigned short)(r + 1);
-            if (s.sb[sr] == s.se[sr]) {
-                do { ++sr; } while (sr < g1 && s.sb[sr] == s.se[sr]);
-                if (sr >= g1) return;
-            }
-            r = s.sb[sr];
-            continue;
-        }
-        s.lS[r] = (short)(num / den);  // num >= 0 here
-        return;
-    }
-}
-
 // One CTA per row.  P1: prune columns that are dominated from both sides by a neighbouring 8-column
-// block (sound: SURVEY Appendix B / DESIGN.md §row pass), compact the survivors.  P2: per-thread
-// stacks over short segments + log2(128) bridging levels.  P3: compact the envelope to global.
-__global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, int n, int row0, int2 *__restrict__ rle,
-                                                int *__restrict__ rle_cnt, const SrmCtl *__restrict__ ctl,
-                                                int respect_stop) {
+// block (sound: DESIGN.md §row pass), compact the survivors.  P2: per-thread stacks over short
+// segments + log2(128) bridging levels.  P3: compact the envelope to global.
+__global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, int n, int row0, int nrows,
+                                                int2 *__restrict__ rle, int *__restrict__ rle_cnt,
+                                                const int *__restrict__ rows, const int *__restrict__ count,
+                                                const SrmCtl *__restrict__ ctl, int respect_stop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
     if (respect_stop && ctl->stop) return;
-    RowSmem s;
-    s.lx = (unsigned short *)smem_raw;
-    s.lc = (short *)(s.lx + n);
-    s.lS = s.lc + n;
+    EnvSmem s;
+    s.x = (unsigned short *)smem_raw;
+    s.c = (short *)(s.x + n);
+    s.S = s.c + n;
     s.sb = sb_;
     s.se = se_;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int total = rows ? *count : nrows;
+    for (int q = blockIdx.x; q < total; q += gridDim.x) {
+        const int r = rows ? rows[q] : q, Y = row0 + r;
+        const short *row = cy + (size_t)r * n;
+        const int nchunks = n >> 8;
+        const int c0 = (w * nchunks) / ROW_NW, c1 = ((w + 1) * nchunks) / ROW_NW;
+        const int rb = c0 << 8;
+        int base = rb, carryM = SRM_BIG;
 
-    const int r = blockIdx.x, Y = row0 + r, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const short *row = cy + (size_t)r * n;
-    const int nchunks = n >> 8;
-    const int c0 = (w * nchunks) / ROW_NW, c1 = ((w + 1) * nchunks) / ROW_NW;
-    const int rb = c0 << 8;
-    int base = rb, carryM = SRM_BIG;
-
-    for (int c = c0; c < c1; ++c) {
-        const int x0 = (c << 8) + lane * 8;
-        int g[8];
-        short cs[8];
-        uint4 v = *reinterpret_cast<const uint4 *>(row + x0);
-        int M = min8_dist(v, Y, g, cs);
-        int ML = __shfl_up_sync(0xffffffffu, M, 1), MR = __shfl_down_sync(0xffffffffu, M, 1);
-        if (lane == 0) {
-            if (c == c0) {
-                ML = SRM_BIG;
-                if (x0 > 0) ML = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 - 8), Y, nullptr, nullptr);
-            } else ML = carryM;
-        }
-        if (lane == 31) {
-            MR = SRM_BIG;
-            if (x0 + 8 < n) MR = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 + 8), Y, nullptr, nullptr);
-        }
-        carryM = __shfl_sync(0xffffffffu, M, 31);
-        const int TL = ML * ML + 225, TR = MR * MR + 225;  // 15^2: farthest column of an adjacent block
-        unsigned live = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            int g2 = g[k] * g[k];
-            bool dead = (g[k] == SRM_BIG) || (g2 >= TL && g2 > TR);
-            live |= dead ? 0u : (1u << k);
-        }
-        int cnt = __popc(live);
-        int incl = warp_incl_scan(cnt, lane);
-        int o = base + incl - cnt;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            if (live & (1u << k)) { s.lx[o] = (unsigned short)(x0 + k); s.lc[o] = cs[k]; ++o; }
-        base += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    __syncwarp();
-
-    // P2a: per-lane stack, in place over its slice of the warp's survivors
-    {
-        const int m = base - rb, q = (m + 31) >> 5;
-        const int beg = rb + min(lane * q, m), end = rb + min((lane + 1) * q, m);
-        int top = beg;
-        for (int i = beg; i < end; ++i) {
-            const int xr = s.lx[i];
-            const short cr = s.lc[i];
-            const int gr = cr - Y, Hr = xr * xr + gr * gr;
-            int num = 0, den = 1;
-            while (top > beg) {
-                int xl = s.lx[top - 1], gl = s.lc[top - 1] - Y;
-                num = Hr - (xl * xl + gl * gl);
-                den = 2 * (xr - xl);
-                if (num < ((int)s.lS[top - 1] + 1) * den) --top; else break;
+        for (int c = c0; c < c1; ++c) {
+            const int x0 = (c << 8) + lane * 8;
+            int g[8];
+            short cs[8];
+            uint4 v = *reinterpret_cast<const uint4 *>(row + x0);
+            int M = min8_dist(v, Y, g, cs);
+            int ML = __shfl_up_sync(0xffffffffu, M, 1), MR = __shfl_down_sync(0xffffffffu, M, 1);
+            if (lane == 0) {
+                if (c == c0) {
+                    ML = SRM_BIG;
+                    if (x0 > 0) ML = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 - 8), Y, nullptr, nullptr);
+                } else ML = carryM;
             }
-            short S = -1;
-            if (top > beg) {
-                if (num >= (n - 1) * den) continue;  // never wins inside the grid
-                S = (short)(num / den);
+            if (lane == 31) {
+                MR = SRM_BIG;
+                if (x0 + 8 < n) MR = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 + 8), Y, nullptr, nullptr);
             }
-            s.lx[top] = (unsigned short)xr; s.lc[top] = cr; s.lS[top] = S;
-            ++top;
+            carryM = __shfl_sync(0xffffffffu, M, 31);
+            const int TL = ML * ML + 225, TR = MR * MR + 225;  // 15^2: farthest column of an adjacent block
+            unsigned live = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int g2 = g[k] * g[k];
+                bool dead = (g[k] == SRM_BIG) || (g2 >= TL && g2 > TR);
+                live |= dead ? 0u : (1u << k);
+            }
+            int cnt = __popc(live);
+            int incl = warp_incl_scan(cnt, lane);
+            int o = base + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (live & (1u << k)) { s.x[o] = (unsigned short)(x0 + k); s.c[o] = cs[k]; ++o; }
+            base += __shfl_sync(0xffffffffu, incl, 31);
         }
-        s.sb[t] = (unsigned short)beg;
-        s.se[t] = (unsigned short)top;
-    }
-    __syncthreads();
+        __syncwarp();
 
-    // P2b: bridge neighbouring groups, doubling the group size each level
-    for (int span = 1; span < ROW_NT; span <<= 1) {
-        if ((t & (2 * span - 1)) == span) merge_groups(s, t - span, t, t + span, Y, n);
+        // P2a: per-lane stack, in place over its slice of the warp's survivors
+        {
+            const int m = base - rb, qq = (m + 31) >> 5;
+            const int beg = rb + min(lane * qq, m), end = rb + min((lane + 1) * qq, m);
+            s.sb[t] = (unsigned short)beg;
+            s.se[t] = (unsigned short)env_lane_stack(s, beg, end, Y, n);
+        }
         __syncthreads();
-    }
 
-    // P3: compact to global run-length form
-    {
-        const int b = s.sb[t], e = s.se[t], cnt = e - b;
-        int incl = warp_incl_scan(cnt, lane);
-        if (lane == 31) wtot[w] = incl;
+        // P2b: bridge neighbouring groups, doubling the group size each level
+        for (int span = 1; span < ROW_NT; span <<= 1) {
+            if ((t & (2 * span - 1)) == span) env_merge(s, t - span, t, t + span, Y, n);
+            __syncthreads();
+        }
+
+        // P3: compact to global run-length form
+        {
+            const int b = s.sb[t], e = s.se[t], cnt = e - b;
+            int incl = warp_incl_scan(cnt, lane);
+            if (lane == 31) wtot[w] = incl;
+            __syncthreads();
+            int off = incl - cnt;
+            for (int k = 0; k < w; ++k) off += wtot[k];
+            int2 *out = rle + (size_t)r * n + off;
+            for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.x[i], s.c[i]), (int)s.S[i] + 1);
+            if (t == ROW_NT - 1) rle_cnt[r] = off + cnt;
+        }
         __syncthreads();
-        int off = incl - cnt;
-        for (int k = 0; k < w; ++k) off += wtot[k];
-        int2 *out = rle + (size_t)r * n + off;
-        for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.lx[i], s.lc[i]), (int)s.lS[i] + 1);
-        if (t == ROW_NT - 1) rle_cnt[r] = off + cnt;
     }
 }
 
@@ -289,12 +223,15 @@ static size_t row_smem_bytes(int n) { return (size_t)n * 6; }
 
 cudaError_t srm_label_setup(int n) {
     cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(n));
-    return e;
+    if (e != cudaSuccess) return e;
+    return srm_band_setup(n);
 }
 
-cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const SrmCtl *ctl,
-                           int respect_stop) {
-    k_row<<<g.nrows(), ROW_NT, row_smem_bytes(g.n), st>>>(cy, g.n, g.row0, rle, rle_cnt, ctl, respect_stop);
+cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const int *rows,
+                           const int *count, const SrmCtl *ctl, int respect_stop) {
+    const int grid = rows ? 148 * 2 : g.nrows();
+    k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(cy, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, ctl,
+                                                     respect_stop);
     return cudaGetLastError();
 }
 

@@ -10,6 +10,7 @@
 // and the CVT energy follows from the same three sums.  Accumulators are fp64 per site
 // (W, X, Y, pad) and are all-reduced across row bands by the caller when sharded.
 #include "srm_common.cuh"
+#include "srm_envelope.cuh"
 
 // ------------------------------------------------------------------ prefix sums (once per call)
 
@@ -69,67 +70,36 @@ void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, do
 // ------------------------------------------------------------------ per-run accumulation
 
 #define ACC_NT 128
-// One warp per row; lanes stride over the row's runs.
+// Robust-path accumulation: one warp per listed row (rows == nullptr: all rows of the band).
 __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt,
                                                 const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                 const int *__restrict__ idmap, int n, int row0, int nrows,
-                                                double *__restrict__ acc, int Kcap, const SrmCtl *__restrict__ ctl,
+                                                double *__restrict__ acc, int Kcap, const int *__restrict__ rows,
+                                                const int *__restrict__ count, const SrmCtl *__restrict__ ctl,
                                                 int want_energy, int respect_stop) {
     if (respect_stop && ctl->stop) return;
     const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5);
-    if (r >= nrows) return;
-    const int Y = row0 + r, cnt = rle_cnt[r];
-    const int2 *rr = rle + (size_t)r * n;
-    const double2 *p2 = P2 + (size_t)r * n;
-    const double *pxx = PXX + (size_t)r * n;
+    const int total = rows ? *count : nrows;
+    const int nwarps = gridDim.x * (ACC_NT / 32);
     double e_loc = 0;
-    double2 carry = make_double2(0, 0);  // prefix at the end of the previous run
-    double carryxx = 0;
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        const bool act = e < cnt;
-        int2 v = act ? rr[e] : make_int2(0, 0);
-        int b = n - 1;
-        if (act && e + 1 < cnt) b = rr[e + 1].y - 1;
-        double2 pb = act ? p2[b] : make_double2(0, 0);
-        double xb = (act && want_energy) ? pxx[b] : 0;
-        double2 pa;
-        pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1);
-        pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);
-        double xa = __shfl_up_sync(0xffffffffu, xb, 1);
-        if (lane == 0) { pa = carry; xa = carryxx; }
-        // last active lane's pb is the carry for the next batch of 32 runs
-        int lastl = min(31, cnt - e0 - 1);
-        carry.x = __shfl_sync(0xffffffffu, pb.x, lastl);
-        carry.y = __shfl_sync(0xffffffffu, pb.y, lastl);
-        carryxx = __shfl_sync(0xffffffffu, xb, lastl);
-        if (act) {
-            const double W = pb.x - pa.x, X = pb.y - pa.y;
-            const int sx = srm_x(v.x), sy = srm_y(v.x);
-            const int id = idmap[(size_t)sy * n + sx];
-            double *a = acc + 4 * (size_t)id;
-            atomicAdd(a, W);
-            atomicAdd(a + 1, X);
-            atomicAdd(a + 2, (double)Y * W);
-            if (want_energy) {
-                const int dy = sy - Y;
-                e_loc += (xb - xa) - 2.0 * (double)sx * X + (double)(sx * sx + dy * dy) * W;
-            }
-        }
+    for (int q = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5); q < total; q += nwarps) {
+        const int r = rows ? rows[q] : q;
+        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, row0 + r, acc,
+                         want_energy, lane);
     }
     if (want_energy) {
         e_loc = warp_sum(e_loc);
-        if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
+        if (lane == 0 && e_loc != 0.0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
     }
 }
 
 void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
-                    const int *idmap, SrmGrid g, double *acc, int Kcap, const SrmCtl *ctl, int want_energy,
-                    int respect_stop) {
-    int rows_per_block = ACC_NT / 32;
-    k_acc<<<(g.nrows() + rows_per_block - 1) / rows_per_block, ACC_NT, 0, st>>>(
-        rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, ctl, want_energy, respect_stop);
+                    const int *idmap, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
+                    const SrmCtl *ctl, int want_energy, int respect_stop) {
+    const int rows_per_block = ACC_NT / 32;
+    const int grid = rows ? 148 : (g.nrows() + rows_per_block - 1) / rows_per_block;
+    k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
+                                   want_energy, respect_stop);
 }
 
 // ------------------------------------------------------------------ block-count scan helper

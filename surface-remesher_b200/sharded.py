@@ -56,6 +56,9 @@ class CudaBandEngine:
     def accumulate(self, want_energy):
         self.ctx.accumulate(want_energy)
 
+    def label_accumulate(self, want_energy):
+        self.ctx.label_accumulate(want_energy)
+
     def acc_tensor(self):
         return self._acc
 
@@ -88,8 +91,11 @@ class ShardedLloyd:
     def step(self):
         """label -> per-band accumulate -> all-reduce -> replicated update."""
         want_energy = (self.it % 10) == 0   # gcvt.cu:1116
-        self.engine.label()
-        self.engine.accumulate(want_energy)
+        if hasattr(self.engine, "label_accumulate"):
+            self.engine.label_accumulate(want_energy)   # fused band kernel
+        else:
+            self.engine.label()
+            self.engine.accumulate(want_energy)
         if self.world > 1:
             self.dist.all_reduce(self.engine.acc_tensor())  # sum
         self.engine.update()

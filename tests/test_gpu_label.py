@@ -8,13 +8,20 @@ import _oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _label(seeds):
+def _label(seeds, robust=None):
+    """Labels through the C ABI; robust=None checks that the fused band kernel and the robust row path agree."""
     import surface_remesher_b200 as S
     n = seeds.shape[0]
-    with S.Context(n) as c:
-        c.set_site_map(np.ascontiguousarray(seeds))
-        c.label()
-        return c.get_labels()
+    out = []
+    for rb in ([False, True] if robust is None else [robust]):
+        with S.Context(n) as c:
+            c.set_option("robust_only", rb)
+            c.set_site_map(np.ascontiguousarray(seeds))
+            c.label()
+            out.append(c.get_labels())
+    if len(out) == 2:
+        assert (out[0] != out[1]).sum() == 0, "band kernel and robust path disagree"
+    return out[0]
 
 
 @pytest.mark.parametrize("n,k,seed", [(256, 1, 0), (256, 2, 1), (256, 50, 2), (256, 4000, 3), (512, 500, 4),
@@ -50,6 +57,23 @@ def test_label_degenerate_layouts():
         got = _label(s)
         exp = O.label_brute(s)
         assert (got != exp).sum() == 0
+
+
+def test_band_kernel_overflow_falls_back_to_robust_path():
+    """Every column live (all sites in a few rows) overflows the band kernel's shared-memory lists:
+    those rows must be handed to the robust path and still be exact."""
+    import surface_remesher_b200 as S
+    n = 1024
+    v = np.full((n, n, 2), I.MARK, np.int16)
+    for y in (3, 500, 1000):
+        v[y, :, 0] = np.arange(n); v[y, :, 1] = y
+    with S.Context(n) as c:
+        c.set_site_map(v)
+        c.label()
+        runs, ovf = c.debug_counts()
+        got = c.get_labels()
+    assert ovf > 0
+    assert (got != O.label_exact(v)).sum() == 0
 
 
 def test_label_row_band_contexts_agree():

@@ -48,13 +48,15 @@ def test_single_step_teacher_forced(kind, n, k, omega):
     assert st["energy"] == np.float32(e) or abs(st["energy"] - e) / e < 1e-6
 
 
-@pytest.mark.parametrize("kind,n,k,iters,stop", [("uniform", 256, 400, 60, True), ("c3", 512, 3000, 40, True),
-                                                  ("c3", 256, 300, 200, True), ("uniform", 512, 1000, 25, False),
-                                                  ("c3", 1024, 5000, 30, True)])
-def test_whole_gcvt_bit_exact(kind, n, k, iters, stop):
+@pytest.mark.parametrize("kind,n,k,iters,stop,robust", [("uniform", 256, 400, 60, True, False), ("c3", 512, 3000, 40, True, False),
+                                                         ("c3", 256, 300, 200, True, False), ("uniform", 512, 1000, 25, False, False),
+                                                         ("c3", 1024, 5000, 30, True, False), ("c3", 512, 3000, 40, True, True),
+                                                         ("uniform", 2048, 40000, 12, False, False)])
+def test_whole_gcvt_bit_exact(kind, n, k, iters, stop, robust):
     import surface_remesher_b200 as S
     dens, mask, seeds = _case(kind, n, k)
     with S.Context(n) as c:
+        c.set_option("robust_only", robust)
         c.set_density(dens); c.set_mask(mask); c.set_site_map(seeds)
         st = c.run(iters, stop_rule=stop)
         lab = c.get_labels()
