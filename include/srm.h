@@ -58,6 +58,9 @@ int srm_version(void);
 int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
              srm_stats *stats);
 
+/* srm_gcvt keeps the device context of its last call for reuse (same n, same device); this frees it. */
+int srm_release_cache(void);
+
 /* discretization_d (discretization.cu:87-120): first triangle (index order) containing the
  * sample (x*scale, y*scale) gives the barycentric interpolation of the vertex weights; 0 if none. */
 int srm_discretize(const double *points, const double *weight, int num_point, const int *triangle, int num_tri,
@@ -108,8 +111,8 @@ int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */
 int srm_iterate(srm_ctx *ctx, int iters, int stop_rule);
 /* Same loop with CUDA events between the stages (measurement only): stage_ms[6] receives the summed device
- * milliseconds of {site bitmap + carries, fused band kernel, robust-path column + row, robust-path accumulate,
- * update + control, whole iteration}. */
+ * milliseconds of {site bitmap + carries, fused band kernel, robust row path, (unused), update + control,
+ * whole iteration}. */
 int srm_iterate_profiled(srm_ctx *ctx, int iters, int stop_rule, float *stage_ms);
 /* Whole gCVT on resident inputs: loop + final labelling. */
 int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);

@@ -45,6 +45,7 @@ def lib():
     L.srm_version.restype = i
     L.srm_gcvt.argtypes = [p, p, p, i, i, i, p]
     L.srm_discretize.argtypes = [p, p, i, p, i, p, d, i]
+    L.srm_release_cache.argtypes = []
     L.srm_seed.argtypes = [p, p, p, i, i, p]
     L.srm_generate_mask.argtypes = [p, p, i, i, d, d, d]
     L.srm_create.argtypes = [C.POINTER(p), i, i, i, i]
@@ -70,7 +71,7 @@ def lib():
     L.srm_debug_counts.argtypes = [p, C.POINTER(C.c_longlong), C.POINTER(i)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
-    for name in ("srm_gcvt", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
+    for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
                  "srm_set_stream", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
@@ -261,7 +262,7 @@ class Context:
     def iterate(self, iters, stop_rule=False):
         _ck(lib().srm_iterate(self._h, int(iters), int(bool(stop_rule))))
 
-    STAGES = ("bitmap+carry", "band_fused", "robust_col_row", "robust_accumulate", "update", "iteration")
+    STAGES = ("bitmap+carry", "band_fused", "robust_rows", "unused", "update", "iteration")
 
     def iterate_profiled(self, iters, stop_rule=False):
         """dict stage -> summed device ms over `iters` iterations (CUDA events between the stages)."""

@@ -15,6 +15,7 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -58,7 +59,7 @@ struct srm_ctx {
     size_t blockcap = 0;
     // labelling state
     uint32_t *bits = nullptr;
-    short *up = nullptr, *dn = nullptr, *cy = nullptr;
+    short *up = nullptr, *dn = nullptr;
     int2 *rle = nullptr;
     int *rle_cnt = nullptr, *idmap = nullptr, *claim = nullptr, *labels = nullptr, *scratch_map = nullptr;
     int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
@@ -90,7 +91,7 @@ static int alloc_sites(srm_ctx *c, int K) {
 static int reset_ctl(srm_ctx *c, int K) {
     SrmCtl h;
     memset(&h, 0, sizeof(h));
-    h.K = K; h.Knext = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
+    h.K = K; h.nlive = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
     CK(cudaMemcpyAsync(c->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // h is a stack object
     c->it_host = 0;
@@ -110,13 +111,6 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
         return fail(SRM_ERR_CUDA, "srm_create: no CUDA device (libsrm has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(SRM_ERR_ARG, "srm_create: device %d of %d", device, ndev);
     CK(cudaSetDevice(device));
-    {   // The accumulate pass reads one 16-byte fp64 prefix pair per run end, scattered over a >1 GB array: with the
-        // default 128-byte L2 fetch granularity every lookup costs a full line of DRAM traffic (measured 621 MB
-        // per launch at 8192^2, ncu).  32-byte granularity fetches the one sector that is needed.
-        const char *env = getenv("SRM_L2_FETCH");
-        size_t gran = env ? (size_t)atoi(env) : 32;
-        if (gran == 32 || gran == 64 || gran == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
-    }
     srm_ctx *c = new srm_ctx();
     c->g.n = n; c->g.row0 = row0; c->g.row1 = row1;
     c->device = device;
@@ -142,7 +136,6 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->bits, NW * sizeof(uint32_t)));
     CKD(cudaMalloc(&c->up, NW * sizeof(short)));
     CKD(cudaMalloc(&c->dn, NW * sizeof(short)));
-    CKD(cudaMalloc(&c->cy, NB * sizeof(short)));
     CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
@@ -167,7 +160,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
-                    c->blockoff, c->bits, c->up, c->dn, c->cy, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
+                    c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
                     c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -227,15 +220,15 @@ extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device
         dmap = c->scratch_map;
     }
     int rc;
-    srm_launch_sites_from_map(c->stream, dmap, c->N, nullptr, c->blockcnt, c->blockoff, c->ctl, 1);
+    srm_launch_sites_from_map(c->stream, dmap, c->N, nullptr, c->blockcnt, c->blockoff, &c->ctl->nlive, 1);
     CK(cudaGetLastError());
     SrmCtl h;
     CK(cudaMemcpyAsync(&h, c->ctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    const int K = h.Knext;
+    const int K = h.nlive;
     rc = alloc_sites(c, K);
     if (rc) return rc;
-    srm_launch_sites_from_map(c->stream, dmap, c->N, c->sites[0], c->blockcnt, c->blockoff, c->ctl, 0);
+    srm_launch_sites_from_map(c->stream, dmap, c->N, c->sites[0], c->blockcnt, c->blockoff, nullptr, 0);
     CK(cudaGetLastError());
     rc = reset_ctl(c, K);
     if (rc) return rc;
@@ -275,11 +268,13 @@ extern "C" int srm_get_sites(srm_ctx *c, int *packed_xy_host, int capacity, int 
     SrmCtl h;
     int rc = fetch_ctl(c, &h);
     if (rc) return rc;
-    *num_out = h.K;
-    if (packed_xy_host) {
-        int k = std::min(capacity, h.K);
-        if (k > 0) CK(cudaMemcpy(packed_xy_host, c->sites[current_buffer(c)], (size_t)k * sizeof(int),
-                                 cudaMemcpyDeviceToHost));
+    *num_out = h.nlive;
+    if (packed_xy_host && h.K > 0) {  // the device list keeps holes for merged sites: filter them here
+        std::vector<int> all((size_t)h.K);
+        CK(cudaMemcpy(all.data(), c->sites[current_buffer(c)], all.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        int k = 0;
+        for (int v : all)
+            if (v != SRM_SENT && k < capacity) packed_xy_host[k++] = v;
     }
     return SRM_OK;
 }
@@ -339,12 +334,8 @@ static int label_with(srm_ctx *c, int buf, int respect_stop, int accumulate, int
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
-    srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, rows, count, c->ctl, respect_stop);
-    CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, rows, count, c->ctl, respect_stop));
-    if (accumulate)
-        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, rows, count, c->ctl,
-                       want_energy, respect_stop);
-    CK(cudaGetLastError());
+    CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
+                      c->acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
     return SRM_OK;
 }
 
@@ -405,8 +396,7 @@ extern "C" int srm_update(srm_ctx *c) {
     CK(cudaSetDevice(c->device));
     const int buf = current_buffer(c);
     srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
-                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt, c->blockoff, (c->it_host % 10) == 0,
-                      0, 0);
+                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, (c->it_host % 10) == 0, 0, 0);
     CK(cudaGetLastError());
     c->labelled = false;
     c->it_host += 1;
@@ -424,8 +414,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
         rc = label_with(c, buf, 1, 1, want_energy);
         if (rc) return rc;
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt,
-                          c->blockoff, want_energy, stop_rule, 1);
+                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
+                          stop_rule, 1);
     }
     CK(cudaGetLastError());
     c->it_host = it;
@@ -439,8 +429,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
 }
 
 // Same loop as srm_iterate with CUDA events between the stages; stage_ms[6] receives the summed device
-// time of {site bitmap + carries, fused band kernel, robust-path column+row, robust-path accumulate,
-// update + control, whole iteration}.
+// time of {site bitmap + carries, fused band kernel, robust row path, (unused), update + control,
+// whole iteration}.
 extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float *stage_ms) {
     int rc = require_ready(c, "srm_iterate_profiled", true);
     if (rc) return rc;
@@ -466,15 +456,13 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
             count = &c->ctl->ovf;
         }
         CK(cudaEventRecord(e[2], c->stream));
-        srm_launch_col(c->stream, c->bits, c->up, c->dn, c->g, c->cy, rows, count, c->ctl, 1);
-        CK(srm_launch_row(c->stream, c->cy, c->g, c->rle, c->rle_cnt, rows, count, c->ctl, 1));
+        CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
+                          c->acc, c->Kcap, c->ctl, 1, want_energy, 1));
         CK(cudaEventRecord(e[3], c->stream));
-        srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, rows, count, c->ctl,
-                       want_energy, 1);
         CK(cudaEventRecord(e[4], c->stream));
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, c->blockcnt,
-                          c->blockoff, want_energy, stop_rule, 1);
+                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
+                          stop_rule, 1);
         CK(cudaEventRecord(e[5], c->stream));
     }
     CK(cudaGetLastError());
@@ -499,7 +487,7 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
 
 static void fill_stats(const SrmCtl &h, srm_stats *s, float ms) {
     if (!s) return;
-    s->iterations = h.it; s->num_sites = h.K; s->stopped = h.stop; s->omega = h.omega; s->energy = h.E; s->ms_device = ms;
+    s->iterations = h.it; s->num_sites = h.nlive; s->stopped = h.stop; s->omega = h.omega; s->energy = h.E; s->ms_device = ms;
 }
 
 extern "C" int srm_get_state(srm_ctx *c, srm_stats *stats) {
@@ -573,6 +561,16 @@ extern "C" int srm_label_jfa(srm_ctx *c, const int *steps, int nsteps, short *ou
 
 // ------------------------------------------------------------------ one-shot drop-ins
 
+static std::mutex g_cache_mu;
+static srm_ctx *g_cache = nullptr;
+static int g_cache_n = 0, g_cache_dev = -1;
+
+extern "C" int srm_release_cache(void) {
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_cache) { srm_destroy(g_cache); g_cache = nullptr; }
+    return SRM_OK;
+}
+
 extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
                         srm_stats *stats) {
     if (!voronoi || !density) return fail(SRM_ERR_ARG, "srm_gcvt: null argument");
@@ -584,9 +582,18 @@ extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned cha
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     double t0 = now(), t1;
 #define TR(what) do { if (trace) { t1 = now(); fprintf(stderr, "[srm_gcvt] %-12s %8.2f ms\n", what, t1 - t0); t0 = t1; } } while (0)
-    srm_ctx *c = nullptr;
-    int rc = srm_create(&c, n, 0, n, dev);
-    if (rc) return rc;
+    // The reference allocates and frees ~46 N bytes of device memory on every call (gcvt.cu:840-903); here the
+    // context of the last call is kept (per process, one at a time) and reused when n and the device match,
+    // so repeated calls pay only for the transfers and the loop.  srm_release_cache() frees it.
+    std::lock_guard<std::mutex> lock(g_cache_mu);
+    if (g_cache && (g_cache_n != n || g_cache_dev != dev)) { srm_destroy(g_cache); g_cache = nullptr; }
+    int rc = SRM_OK;
+    if (!g_cache) {
+        rc = srm_create(&g_cache, n, 0, n, dev);
+        if (rc) { g_cache = nullptr; return rc; }
+        g_cache_n = n; g_cache_dev = dev;
+    }
+    srm_ctx *c = g_cache;
     TR("create");
     rc = srm_set_density(c, density, 0);
     TR("density");
@@ -598,8 +605,7 @@ extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned cha
     TR("run");
     if (!rc) rc = srm_get_labels(c, voronoi, 0);
     TR("get_labels");
-    srm_destroy(c);
-    TR("destroy");
+    if (rc) { srm_destroy(g_cache); g_cache = nullptr; }  // do not keep a context in an unknown state
 #undef TR
     return rc;
 }

@@ -21,7 +21,7 @@
 //     The output pass writes the runs and, in accumulate mode, adds the fp64 prefix differences of each
 //     run to its site's accumulators (centroid + energy).
 // A band whose list exceeds CL entries, or a row whose envelope exceeds the buffer, is handed to the
-// robust path (k_col/k_row/k_acc).
+// robust path (k_row in srm_label.cu).
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
 

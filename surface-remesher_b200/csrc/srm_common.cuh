@@ -11,8 +11,10 @@
 
 // Device-side loop state (gcvt.cu:1105-1142 keeps these on the host; here the host never syncs).
 struct SrmCtl {
-    int K;          // live sites
-    int Knext;      // written by the update compaction, latched by k_control
+    int K;          // length of the site list (fixed; merged sites become SRM_SENT holes, gcvt.cu:779-780)
+    int nlive;      // live sites after the last update
+    int live_acc;   // live-site counter of the running update
+    int ticket;     // last-block-done counter of the running update
     int stop;       // reference stopping rule fired
     int it;         // iterations done (gcvtIterations)
     float omega;    // pbaOmega
@@ -69,10 +71,10 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
                             double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
                             int dbg = 0);
 // robust path, driven by a row list (rows == nullptr: every row of the band)
-void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
-                    const int *rows, const int *count, const SrmCtl *ctl, int respect_stop);
-cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const int *rows,
-                           const int *count, const SrmCtl *ctl, int respect_stop);
+cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
+                           int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
+                           const int *idmap, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
+                           int respect_stop);
 cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels);
 cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes
 
@@ -81,10 +83,10 @@ void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const 
                     const int *idmap, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
                     const SrmCtl *ctl, int want_energy, int respect_stop);
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int *blockcnt,
-                       int *blockoff, int want_energy, int stop_rule, int respect_stop);
+                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
+                       int stop_rule, int respect_stop);
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
-                               int *blockoff, SrmCtl *ctl, int count_only);
+                               int *blockoff, int *total_out, int count_only);
 void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out);
 void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step);
 void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map);

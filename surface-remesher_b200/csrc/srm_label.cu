@@ -6,9 +6,10 @@
 //
 //   sites (K packed int32) --k_bits--> column bitmap  bits[(y>>5)*n + x] bit (y&31)     N/8 B
 //   k_carry: per column, nearest site row above / below every 32-row word                N/8 B
-//   k_col:   cy[Y][x] = row of the column candidate c(x,Y)                               2 B/px
-//   k_row:   per row, lower envelope of the parabolas (X-x)^2+(cy[x]-Y)^2 with INTEGER
-//            breakpoints -> run-length labels  rle[row] = {(site, first X)}             ~8 B/run
+//   k_band (srm_band.cu): per 16-row band, candidates straight from the bitmap, per row the lower
+//            envelope of the parabolas (X-x)^2+(c(x,Y)-Y)^2 with INTEGER breakpoints
+//            -> run-length labels  rle[row] = {(site, first X)}  (+ fused accumulation)   ~8 B/run
+//   k_row:   the same result for rows that overflow k_band's shared-memory budget (worst-case capacity)
 //   k_expand (final labelling only): runs -> dense short2 labels                         4 B/px
 //
 // All arithmetic is integer; ties follow the reference (column tie: gcvt.cu:97-119 + :172-216;
@@ -25,6 +26,7 @@ __global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32
     int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     int p = sites[id];
+    if (p == SRM_SENT) return;  // merged away
     int x = srm_x(p), y = srm_y(p);
     atomicOr(&bits[(size_t)(y >> 5) * n + x], 1u << (y & 31));
     size_t i = (size_t)y * n + x;
@@ -40,10 +42,8 @@ void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, i
     k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop);
 }
 
-// Per column: up[j][x] = largest site row < 32j, dn[j][x] = smallest site row >= 32(j+1) (MARK if none).
-// This is the in-GPU analogue of kernelPropagateInterband (gcvt.cu:121-170) and, for row-band
-// sharding, what makes halo exchange unnecessary: every band scans the replicated bitmap.
-__global__ void k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up, short *__restrict__ dn,
+// Generic form (any n): one thread per column, one sweep per direction.
+__global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__restrict__ up, short *__restrict__ dn,
                         const SrmCtl *__restrict__ ctl, int respect_stop) {
     if (respect_stop && ctl->stop) return;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,44 +70,73 @@ __global__ void k_carry(const uint32_t *__restrict__ bits, int n, short *__restr
     }
 }
 
+// Per column: up[j][x] = largest site row < 32j, dn[j][x] = smallest site row >= 32(j+1) (MARK if none).
+// This is the in-GPU analogue of kernelPropagateInterband (gcvt.cu:121-170) and, for row-band
+// sharding, what makes halo exchange unnecessary: every band scans the replicated bitmap.
+// A CTA owns 32 columns; its 8 warps own 8 segments of the column's word-rows.  Each thread scans its
+// segment once (words kept in registers), segment summaries meet in shared memory, then the thread
+// writes both carries of its words.
+#define CARRY_SEG 8
+template <int WPS>  // words per segment held in registers
+__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up,
+                                                          short *__restrict__ dn, const SrmCtl *__restrict__ ctl,
+                                                          int respect_stop) {
+    __shared__ short s_last[CARRY_SEG][32], s_first[CARRY_SEG][32];
+    if (respect_stop && ctl->stop) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
+    const int j0 = seg * WPS;
+    uint32_t w[WPS];
+    int last = SRM_MARK, first = SRM_MARK;
+#pragma unroll
+    for (int k = 0; k < WPS; ++k) {
+        w[k] = bits[(size_t)(j0 + k) * n + x];
+        if (w[k]) {
+            last = 32 * (j0 + k) + 31 - __clz(w[k]);
+            if (first == SRM_MARK) first = 32 * (j0 + k) + __ffs(w[k]) - 1;
+        }
+    }
+    s_last[seg][threadIdx.x] = (short)last;
+    s_first[seg][threadIdx.x] = (short)first;
+    __syncthreads();
+    int cu = SRM_MARK, cd = SRM_MARK;  // nearest site row above / below this segment
+    for (int q = 0; q < seg; ++q) { const int v = s_last[q][threadIdx.x]; if (v != SRM_MARK) cu = v; }
+    for (int q = CARRY_SEG - 1; q > seg; --q) { const int v = s_first[q][threadIdx.x]; if (v != SRM_MARK) cd = v; }
+#pragma unroll
+    for (int k = 0; k < WPS; ++k) {
+        up[(size_t)(j0 + k) * n + x] = (short)cu;
+        if (w[k]) cu = 32 * (j0 + k) + 31 - __clz(w[k]);
+    }
+#pragma unroll
+    for (int k = WPS - 1; k >= 0; --k) {
+        dn[(size_t)(j0 + k) * n + x] = (short)cd;
+        if (w[k]) cd = 32 * (j0 + k) + __ffs(w[k]) - 1;
+    }
+}
+
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
                       int respect_stop) {
-    dim3 grid((n + 63) / 64, 2);
-    k_carry<<<grid, 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop);
+    dim3 grid(n / 32), block(32, CARRY_SEG);
+    const int wps = (n >> 5) / CARRY_SEG;  // n multiple of 256 -> integral
+    switch (wps) {
+        case 1: k_carry<1><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 2: k_carry<2><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 3: k_carry<3><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 4: k_carry<4><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 8: k_carry<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 16: k_carry<16><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 32: k_carry<32><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 64: k_carry<64><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        case 128: k_carry<128><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        default: k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+    }
 }
 
 // ------------------------------------------------------------------ robust row path (fallback)
 //
-// k_col + k_row handle ANY row with worst-case capacity (every column live): cy row -> prune ->
-// 128 thread stacks -> 7 bridging levels -> runs.  The fused band kernel (srm_band.cu) is the fast
-// path; rows whose candidate lists overflow its shared-memory budget are appended to a row list and
-// processed here.  rows == nullptr means "all rows of the band" (used by tests to pin this path).
-
-// cy[r][x] for the listed rows.
-__global__ void k_col(const uint32_t *__restrict__ bits, const short *__restrict__ up, const short *__restrict__ dn,
-                      int n, int row0, int nrows, short *__restrict__ cy, const int *__restrict__ rows,
-                      const int *__restrict__ count, const SrmCtl *__restrict__ ctl, int respect_stop) {
-    if (respect_stop && ctl->stop) return;
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= n) return;
-    const int total = rows ? *count : nrows;
-    for (int q = blockIdx.y; q < total; q += gridDim.y) {
-        const int r = rows ? rows[q] : q, Y = row0 + r, j = Y >> 5, k = Y & 31;
-        const size_t o = (size_t)j * n + x;
-        const uint32_t w = bits[o];
-        const uint32_t mlo = w & (0xffffffffu >> (31 - k));
-        const uint32_t mhi = (k == 31) ? 0u : (w & (0xffffffffu << (k + 1)));
-        const int U = mlo ? 32 * j + 31 - __clz(mlo) : (int)up[o];
-        const int D = mhi ? 32 * j + __ffs(mhi) - 1 : (int)dn[o];
-        cy[(size_t)r * n + x] = (short)srm_choose_col(U, D, Y);
-    }
-}
-
-void srm_launch_col(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, short *cy,
-                    const int *rows, const int *count, const SrmCtl *ctl, int respect_stop) {
-    dim3 grid((g.n + 127) / 128, rows ? 16 : min(g.nrows(), 2048));
-    k_col<<<grid, 128, 0, st>>>(bits, up, dn, g.n, g.row0, g.nrows(), cy, rows, count, ctl, respect_stop);
-}
+// k_row handles ANY row with worst-case capacity (every column live): column candidates of the row from
+// the bitmap -> prune -> 128 thread stacks -> 7 bridging levels -> runs (-> accumulate).  The fused band
+// kernel (srm_band.cu) is the fast path; rows that overflow its shared-memory budget are appended to a
+// row list and processed here.  rows == nullptr means "all rows of the band" (tests pin this path so).
 
 #define ROW_NT 128
 #define ROW_NW (ROW_NT / 32)
@@ -128,16 +157,20 @@ __device__ __forceinline__ int min8_dist(uint4 v, int Y, int *g, short *cs) {
 // One CTA per row.  P1: prune columns that are dominated from both sides by a neighbouring 8-column
 // block (sound: DESIGN.md §row pass), compact the survivors.  P2: per-thread stacks over short
 // segments + log2(128) bridging levels.  P3: compact the envelope to global.
-__global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, int n, int row0, int nrows,
-                                                int2 *__restrict__ rle, int *__restrict__ rle_cnt,
-                                                const int *__restrict__ rows, const int *__restrict__ count,
-                                                const SrmCtl *__restrict__ ctl, int respect_stop) {
+__global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                                const short *__restrict__ dn, int n, int row0, int nrows, int2 *rle,
+                                                int *__restrict__ rle_cnt, const int *__restrict__ rows,
+                                                const int *__restrict__ count, const double2 *__restrict__ P2,
+                                                const double *__restrict__ PXX, const int *__restrict__ idmap,
+                                                double *__restrict__ acc, int Kcap, const SrmCtl *__restrict__ ctl,
+                                                int accumulate, int want_energy, int respect_stop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
     if (respect_stop && ctl->stop) return;
     EnvSmem s;
-    s.x = (unsigned short *)smem_raw;
+    short *cyrow = (short *)smem_raw;  // column candidates of the row
+    s.x = (unsigned short *)(cyrow + n);
     s.c = (short *)(s.x + n);
     s.S = s.c + n;
     s.sb = sb_;
@@ -146,7 +179,20 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, in
     const int total = rows ? *count : nrows;
     for (int q = blockIdx.x; q < total; q += gridDim.x) {
         const int r = rows ? rows[q] : q, Y = row0 + r;
-        const short *row = cy + (size_t)r * n;
+        {   // column pass of this row (semantics of gcvt.cu:77-216): nearest site above / below from the bitmap
+            const int j = Y >> 5, k = Y & 31;
+            for (int x = t; x < n; x += ROW_NT) {
+                const size_t o = (size_t)j * n + x;
+                const uint32_t wd = bits[o];
+                const uint32_t mlo = wd & (0xffffffffu >> (31 - k));
+                const uint32_t mhi = (k == 31) ? 0u : (wd & (0xffffffffu << (k + 1)));
+                const int U = mlo ? 32 * j + 31 - __clz(mlo) : (int)up[o];
+                const int D = mhi ? 32 * j + __ffs(mhi) - 1 : (int)dn[o];
+                cyrow[x] = (short)srm_choose_col(U, D, Y);
+            }
+        }
+        __syncthreads();
+        const short *row = cyrow;
         const int nchunks = n >> 8;
         const int c0 = (w * nchunks) / ROW_NW, c1 = ((w + 1) * nchunks) / ROW_NW;
         const int rb = c0 << 8;
@@ -213,13 +259,22 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const short *__restrict__ cy, in
             for (int k = 0; k < w; ++k) off += wtot[k];
             int2 *out = rle + (size_t)r * n + off;
             for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.x[i], s.c[i]), (int)s.S[i] + 1);
-            if (t == ROW_NT - 1) rle_cnt[r] = off + cnt;
+            if (t == ROW_NT - 1) { rle_cnt[r] = off + cnt; wtot[0] = off + cnt; }
+        }
+        __syncthreads();
+        if (accumulate && w == 0) {
+            double e_loc = acc_row(rle + (size_t)r * n, wtot[0], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, Y, acc,
+                                   want_energy, lane);
+            if (want_energy) {
+                e_loc = warp_sum(e_loc);
+                if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
+            }
         }
         __syncthreads();
     }
 }
 
-static size_t row_smem_bytes(int n) { return (size_t)n * 6; }
+static size_t row_smem_bytes(int n) { return (size_t)n * 8; }
 
 cudaError_t srm_label_setup(int n) {
     cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(n));
@@ -227,11 +282,13 @@ cudaError_t srm_label_setup(int n) {
     return srm_band_setup(n);
 }
 
-cudaError_t srm_launch_row(cudaStream_t st, const short *cy, SrmGrid g, int2 *rle, int *rle_cnt, const int *rows,
-                           const int *count, const SrmCtl *ctl, int respect_stop) {
-    const int grid = rows ? 148 * 2 : g.nrows();
-    k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(cy, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, ctl,
-                                                     respect_stop);
+cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
+                           int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
+                           const int *idmap, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
+                           int respect_stop) {
+    const int grid = rows ? 148 : g.nrows();
+    k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, P2,
+                                                     PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop);
     return cudaGetLastError();
 }
 
@@ -355,7 +412,7 @@ __global__ void k_scatter_sites(const int *__restrict__ sites, const SrmCtl *__r
     int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     int p = sites[id];
-    map[(size_t)srm_y(p) * n + srm_x(p)] = p;
+    if (p != SRM_SENT) map[(size_t)srm_y(p) * n + srm_x(p)] = p;
 }
 
 void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map) {

@@ -138,8 +138,9 @@ void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, i
 // kernelUpdateSites (gcvt.cu:753-781): centroid, over-relaxation, round, clamp, reject.  The float
 // expression is written with the roundings nvcc produced for the reference (FADD, FFMA, FADD,
 // F2I.TRUNC; checked in the SASS of oracle/_ref).  Collisions: every site claims its target pixel
-// with atomicMin(id); the smallest id survives (the reference merges sites the same way, by
-// overwriting one pixel, gcvt.cu:779-780).
+// with atomicMin(id); the smallest id survives and the others become holes (SRM_SENT) in the list —
+// the reference merges sites the same way, by overwriting one pixel (gcvt.cu:779-780).  The list is
+// never compacted, so ids (accumulator slots) are stable and identical on every rank.
 __global__ void k_update_pos(const int *__restrict__ sites, const double *__restrict__ acc,
                              const float *__restrict__ density, const unsigned char *__restrict__ mask, int n,
                              const SrmCtl *__restrict__ ctl, int *__restrict__ newpos, int *claim, int respect_stop) {
@@ -147,6 +148,7 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *__rest
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     const int p = sites[id];
+    if (p == SRM_SENT) { newpos[id] = SRM_SENT; return; }
     const int tx = srm_x(p), ty = srm_y(p);
     int rx = tx, ry = ty;
     if (!(mask && mask[(size_t)ty * n + tx])) {
@@ -166,47 +168,36 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *__rest
 }
 
 #define UPD_NT 256
-__global__ void __launch_bounds__(UPD_NT) k_update_count(const int *__restrict__ newpos, const int *__restrict__ claim,
-                                                         int n, const SrmCtl *__restrict__ ctl, int *blockcnt,
-                                                         int respect_stop) {
-    if (respect_stop && ctl->stop) return;
+// Resolve the claims, clear the accumulators, and — in the last block to finish — run the loop control of
+// gCVT (gcvt.cu:1116-1140) on device: latch the energy, count the iteration, every 10th iteration update omega
+// and apply the stopping rule.
+__global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict__ newpos, const int *__restrict__ claim,
+                                                           int n, SrmCtl *ctl, int *__restrict__ sites_out,
+                                                           double *__restrict__ acc, int Kcap, int want_energy,
+                                                           int stop_rule, int respect_stop) {
+    __shared__ int is_last;
+    if (respect_stop && ctl->stop) return;  // set only by a previous launch's last block
     const int id = blockIdx.x * UPD_NT + threadIdx.x;
-    int flag = 0;
+    int alive = 0;
     if (id < ctl->K) {
-        int p = newpos[id];
-        flag = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
-    }
-    int c = __syncthreads_count(flag);
-    if (threadIdx.x == 0) blockcnt[blockIdx.x] = c;
-}
-
-__global__ void __launch_bounds__(UPD_NT) k_update_write(const int *__restrict__ newpos, const int *__restrict__ claim,
-                                                         int n, const SrmCtl *__restrict__ ctl,
-                                                         const int *__restrict__ blockoff, int *__restrict__ sites_out,
-                                                         double *__restrict__ acc, int respect_stop) {
-    __shared__ int wtot[UPD_NT / 32];
-    if (respect_stop && ctl->stop) return;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int id = blockIdx.x * UPD_NT + t;
-    int flag = 0, p = 0;
-    if (id < ctl->K) {
-        p = newpos[id];
-        flag = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
+        const int p = newpos[id];
+        if (p != SRM_SENT) alive = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
+        sites_out[id] = alive ? p : SRM_SENT;
         double *a = acc + 4 * (size_t)id;  // clear for the next iteration
         a[0] = 0; a[1] = 0; a[2] = 0; a[3] = 0;
     }
-    int incl = warp_incl_scan(flag, lane);
-    if (lane == 31) wtot[w] = incl;
+    const int c = __syncthreads_count(alive);
+    if (threadIdx.x == 0) {
+        if (c) atomicAdd(&ctl->live_acc, c);
+        __threadfence();
+        is_last = atomicAdd(&ctl->ticket, 1) == (int)gridDim.x - 1;
+    }
     __syncthreads();
-    int off = blockoff[blockIdx.x] + incl - flag;
-    for (int k = 0; k < w; ++k) off += wtot[k];
-    if (flag) sites_out[off] = p;
-}
-
-// Loop control of gCVT (gcvt.cu:1116-1140), on device.  `it_done` = gcvtIterations after this iteration.
-__global__ void k_control(SrmCtl *ctl, double *acc_energy, int n, int want_energy, int stop_rule, int respect_stop) {
-    if (respect_stop && ctl->stop) return;
-    ctl->K = ctl->Knext;
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    ctl->nlive = atomicExch(&ctl->live_acc, 0);
+    ctl->ticket = 0;
+    double *acc_energy = acc + 4 * (size_t)Kcap;
     if (want_energy) {
         ctl->E = (float)(acc_energy[0] / ((double)n * (double)n));
         acc_energy[0] = 0;
@@ -224,17 +215,12 @@ __global__ void k_control(SrmCtl *ctl, double *acc_energy, int n, int want_energ
 }
 
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int *blockcnt,
-                       int *blockoff, int want_energy, int stop_rule, int respect_stop) {
-    if (Kcap > 0) {
-        const int nb = (Kcap + UPD_NT - 1) / UPD_NT;
-        k_update_pos<<<(Kcap + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim,
-                                                          respect_stop);
-        k_update_count<<<nb, UPD_NT, 0, st>>>(newpos, claim, n, ctl, blockcnt, respect_stop);
-        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, &ctl->Knext);
-        k_update_write<<<nb, UPD_NT, 0, st>>>(newpos, claim, n, ctl, blockoff, sites_out, acc, respect_stop);
-    }
-    k_control<<<1, 1, 0, st>>>(ctl, acc + 4 * (size_t)Kcap, n, want_energy, stop_rule, respect_stop);
+                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
+                       int stop_rule, int respect_stop) {
+    const int k1 = Kcap > 0 ? Kcap : 1;
+    k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop);
+    k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
+                                                                     stop_rule, respect_stop);
 }
 
 // ------------------------------------------------------------------ dense seed map -> site list
@@ -284,15 +270,15 @@ __global__ void __launch_bounds__(SFM_NT) k_sites_write(const int4 *__restrict__
     if (f[3]) sites[off++] = v.w;
 }
 
-// count_only != 0: fill blockcnt/blockoff and ctl->Knext (the caller sizes the site arrays from it);
+// count_only != 0: fill blockcnt/blockoff and *total_out (the caller sizes the site arrays from it);
 // count_only == 0: blockoff must hold the scan; writes the list.
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
-                               int *blockoff, SrmCtl *ctl, int count_only) {
+                               int *blockoff, int *total_out, int count_only) {
     const size_t n4 = N / 4;
     const int nb = (int)((n4 + SFM_NT - 1) / SFM_NT);
     if (count_only) {
         k_sites_count<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockcnt);
-        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, &ctl->Knext);
+        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, total_out);
     } else {
         k_sites_write<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockoff, sites_out);
     }

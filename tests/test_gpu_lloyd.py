@@ -205,7 +205,8 @@ def test_full_size_properties(n, k, kind):
     d_lab = (l[:, 0] - px) ** 2 + (l[:, 1] - py) ** 2
     assert np.array_equal(d_lab, np.rint(d_true ** 2).astype(np.int64))
     # (3)
-    W = acc[0:4 * K:4].sum(); X = acc[1:4 * K:4].sum(); Y = acc[2:4 * K:4].sum()
+    kc = (cnt - 4) // 4   # accumulator slots = initial list length (merged sites leave holes, ids are stable)
+    W = acc[0:4 * kc:4].sum(); X = acc[1:4 * kc:4].sum(); Y = acc[2:4 * kc:4].sum()
     d64 = dens.astype(np.float64)
     assert abs(W - d64.sum()) / d64.sum() < 1e-12
     assert abs(X - (d64.sum(0) * np.arange(n)).sum()) / X < 1e-12
