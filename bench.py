@@ -237,7 +237,7 @@ def run_ours(args):
                    "stop_rule": "off (fixed step count); energy every 10th step like the reference"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "iterations_per_call": e2e_iters, "api": "gCVT(host buffers)" if world == 1 else "ShardedLloyd(host buffers)"},
-        "gpu_launches": 10 * K * world,
+        "gpu_launches": 6 * K * world,  # k_bits, k_carry, k_band, k_row, k_update_pos, k_update_resolve per step and rank
         "clocks": clocks,
     }
     if stage is not None:
