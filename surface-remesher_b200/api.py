@@ -27,7 +27,8 @@ class Stats(C.Structure):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsrm.so")
+    # SRM_LIB: alternative build of the same library (kernel-variant A/B measurements only)
+    return os.environ.get("SRM_LIB") or os.path.join(_HERE, "libsrm.so")
 
 
 def lib():

@@ -292,6 +292,16 @@ extern "C" int srm_debug_counts(srm_ctx *c, long long *total_runs, int *overflow
     SrmCtl hc;
     CK(cudaMemcpy(&hc, c->ctl, sizeof(hc), cudaMemcpyDeviceToHost));
     *overflow_rows = c->robust_only ? c->g.nrows() : hc.ovf;
+    if (c->dbg_stats & 1) {
+        const unsigned long long *p = hc.prof;
+        const double tot = (double)(p[0] + p[1] + p[2] + p[3] + p[4] + p[5]);
+        fprintf(stderr, "[srm prof] warp-cycles: phaseA %.1f%% prefilter0 %.1f%% plain0 %.1f%% rounds %.1f%% move %.1f%% output %.1f%% | "
+                        "prefilter survivors/row %.0f (%llu rows) plain survivors/row %.0f (%llu rows) | round steps/row %.1f passes/row %.2f "
+                        "envelope/row %.0f\n",
+                100 * p[0] / tot, 100 * p[1] / tot, 100 * p[2] / tot, 100 * p[3] / tot, 100 * p[4] / tot, 100 * p[5] / tot,
+                p[9] ? (double)p[8] / p[9] : 0.0, p[9], p[11] ? (double)p[10] / p[11] : 0.0, p[11],
+                (double)p[12] / (p[9] + p[11] + 1e-9), (double)p[13] / (p[9] + p[11] + 1e-9), (double)p[14] / (p[9] + p[11] + 1e-9));
+    }
     if (c->dbg_stats)
         fprintf(stderr, "[srm dbg] band list: max %d mean %.1f (%d bands) | row survivors: max %d mean %.1f (%d rows)\n",
                 hc.dbg[0], hc.dbg[2] ? (double)hc.dbg[1] / hc.dbg[2] : 0.0, hc.dbg[2], hc.dbg[3],
@@ -307,6 +317,7 @@ extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
         c->dbg_stats = value;
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaMemset(c->ctl->dbg, 0, sizeof(c->ctl->dbg)));
+        CK(cudaMemset(c->ctl->prof, 0, sizeof(c->ctl->prof)));
         return SRM_OK;
     }
     return fail(SRM_ERR_ARG, "srm_set_option: unknown option %s", name);

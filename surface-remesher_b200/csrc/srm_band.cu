@@ -85,32 +85,29 @@ __device__ __forceinline__ unsigned live_mask(const Col8 &c, int ML, int MR) {
     return live;
 }
 
-// Row candidate of a band-list entry for row Y = Y0 + k (Appendix A2 column rule).
+// Row candidate of a band-list entry for row Y = Y0 + k (Appendix A2 column rule), branch-free: U = nearest
+// site row <= Y, D = nearest > Y (in-band bits override the band-level U, D), nearer wins, tie -> D iff it lies
+// in Y's 64-row band (semantics of kernelFloodDown/Up + kernelPropagateInterband + kernelUpdateVertical).
 __device__ __forceinline__ int row_candidate(int U, int D, uint32_t inb, int Y0, int k, int Y) {
-    if (inb) {
-        const uint32_t lo = inb & (0xffffffffu >> (31 - k));
-        const uint32_t hi = (k == 31) ? 0u : (inb & (0xffffffffu << (k + 1)));
-        if (lo) U = Y0 + 31 - __clz(lo);
-        if (hi) D = Y0 + __ffs(hi) - 1;
-    }
-    return srm_choose_col(U, D, Y);
-}
-
-// floor(num/den) for 0 <= num < (n-1)*den, den in [2, 65534]: approximate float quotient (|error| <= 1) + fix-up
-__device__ __forceinline__ int floordiv_pos(int num, int den) {
-    int q = __float2int_rz(__fdividef(__int2float_rz(num), __int2float_rn(den)));
-    const int r = num - q * den;
-    if (r < 0) --q;
-    else if (r >= den) ++q;
-    return q;
+    const uint32_t lo = inb & (0xffffffffu >> (31 - k));
+    const uint32_t hi = inb & ~(0xffffffffu >> (31 - k));
+    U = lo ? Y0 + 31 - __clz(lo) : U;
+    D = hi ? Y0 + __ffs(hi) - 1 : D;
+    const int du = (U == SRM_MARK) ? SRM_BIG : Y - U, dd = (D == SRM_MARK) ? SRM_BIG : D - Y;
+    const bool pickD = dd < du || (dd == du && (D >> SRM_TIE_BAND_SHIFT) == (Y >> SRM_TIE_BAND_SHIFT));
+    return pickD ? D : U;
 }
 
 // Integer breakpoint between neighbours p < q of a row: p wins (ties included, smallest x first, reference
 // kernelColor gcvt.cu:449-466) exactly for X <= B = floor((H_q - H_p) / (2 (x_q - x_p))), clamped to [-1, n-1].
+// Branch-free (so that independent evaluations interleave): float quotient estimate, |error| <= 1 whenever the
+// true quotient is below n, exact +-1 fix-up, clamps.  num < 0 gives estimate 0, remainder < 0, hence -1.
 __device__ __forceinline__ int breakpoint(int num, int den, int n) {
-    if (num < 0) return -1;
-    if (num >= (n - 1) * den) return n - 1;
-    return floordiv_pos(num, den);
+    int q = __float2int_rz(__fdividef(__int2float_rz(max(num, 0)), __int2float_rn(den)));
+    q = min(q, n);                       // q * den <= 32768 * 65534 < 2^31
+    const int r = num - q * den;
+    q += (int)(r >= den) - (int)(r < 0);
+    return min(q, n - 1);
 }
 
 // Candidate of band-list entry i for row Y = Y0 + k: packed x | c << 16 and H = x^2 + (c - Y)^2.
@@ -133,10 +130,11 @@ struct RoundStep {
     int B, Bc;
     bool owned, keep;
 };
-__device__ __forceinline__ RoundStep round_step(bool valid, int x, int H, int lane, int n, int &carryB) {
+__device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
+                                                int &carryB) {
     RoundStep r;
-    const int xn = __shfl_down_sync(0xffffffffu, x, 1), Hn = __shfl_down_sync(0xffffffffu, H, 1);
-    const bool validn = __shfl_down_sync(0xffffffffu, (int)valid, 1) != 0;
+    const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
+    const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
     r.owned = valid && lane < 31;
     r.B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
     r.Bc = __shfl_up_sync(0xffffffffu, r.B, 1);
@@ -146,7 +144,50 @@ __device__ __forceinline__ RoundStep round_step(bool valid, int x, int H, int la
     return r;
 }
 
-template <int RPW, int C>
+// A dominance round over one chunk, with in-chunk Gauss-Seidel: after the parallel (Jacobi) test, lanes that
+// survive relink to their nearest surviving neighbours inside the chunk and are re-tested until the chunk is stable,
+// so a cascade of dominated elements inside 31 neighbours collapses in one pass instead of one pass per link.
+// Every test uses real candidates as dominators, so every drop is sound.  The carry handed to the next chunk is
+// the breakpoint of (last owned element, lookahead element) from the Jacobi step: a valid bound either way.
+template <int MAX_INNER>
+__device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
+                                            int &carryB) {
+    const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
+    const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
+    const bool owned = valid && lane < 31;
+    int B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
+    int Bc = __shfl_up_sync(0xffffffffu, B, 1);
+    if (lane == 0) Bc = carryB;
+    carryB = __shfl_sync(0xffffffffu, B, 30);
+    bool keep = owned && B > Bc && Bc < n - 1;
+    unsigned bal = __ballot_sync(0xffffffffu, keep);
+    unsigned prevbal = __ballot_sync(0xffffffffu, owned);
+    const bool look = __shfl_sync(0xffffffffu, (int)valid, 31) != 0;  // the lookahead element exists
+#pragma unroll 1
+    for (int inner = 0; inner < MAX_INNER && bal != prevbal; ++inner) {  // something was dropped: relink, re-test (uniform)
+        prevbal = bal;
+        const unsigned link = bal | (look ? 0x80000000u : 0u);
+        const unsigned right = (lane < 31) ? (link >> (lane + 1)) : 0u;
+        const unsigned left = bal & ((1u << lane) - 1u);
+        const int nl = right ? lane + __ffs(right) : 0;     // nearest kept lane to the right (or the lookahead)
+        const int pl = left ? 31 - __clz(left) : 0;         // nearest kept lane to the left
+        const unsigned vr = __shfl_sync(0xffffffffu, v, nl);
+        const int xr = (int)(vr & 0xffffu), gr = (int)(vr >> 16) - Y, Hr = xr * xr + gr * gr;
+        const int Bn = right ? breakpoint(Hr - H, 2 * (xr - x), n) : n - 1;  // against my nearest kept right neighbour
+        const int Bl = __shfl_sync(0xffffffffu, Bn, pl);  // B(nearest kept left neighbour, me): just computed against me
+        B = min(B, Bn);                 // both are bounds by real candidates to my right
+        if (left) Bc = max(Bc, Bl);     // likewise on the left (without a kept left lane the Jacobi bound stays)
+        keep = keep && B > Bc && Bc < n - 1;
+        bal = __ballot_sync(0xffffffffu, keep);
+    }
+    return keep;
+}
+
+#define PROF_T0() long long t0__ = (dbg & 1) ? clock64() : 0
+#define PROF_ADD(slot) do { if (dbg & 1) { long long t1__ = clock64(); if (lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
+#define PROF_CNT(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(v)); } while (0)
+
+template <int RPW, int C, int GS0, int GS1>
 __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
                                                   const short *__restrict__ dn, int n, int row0, int CL,
                                                   int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
@@ -170,6 +211,7 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
     const int nb = n >> 3;
     const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
 
+    PROF_T0();
     // ---- Phase A, pass 1: live mask of every 8-column block (30 owned blocks per step + one halo block each side)
     int mycount = 0;
     for (int b0 = bw0; b0 < bw1; b0 += 30) {
@@ -219,8 +261,12 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
         }
     }
     __syncthreads();
+    PROF_ADD(0);   // phase A
 
-    // ---- Phase B: warp w computes the envelopes of rows rb + w*RPW .. +RPW-1 by dominance rounds
+    // ---- Phase B: warp w computes the envelopes of rows rb + w*RPW .. +RPW-1 by dominance rounds.
+    // Every loop below handles TWO 31-element chunks per iteration: the chunks are independent up to one carry
+    // shuffle, so their shared-memory / global loads, breakpoint divisions and shuffles overlap (the kernel is
+    // latency bound: ncu short/long scoreboard stalls, profiles/r1_ncu_full_summary.md).
     unsigned *buf = buf0 + (size_t)w * C;
     const unsigned lt = (1u << lane) - 1u;
     double e_loc = 0;
@@ -230,42 +276,52 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
         bool overflow = false;
         for (;;) {
             // round 0: candidates of the band list, tested against their list neighbours, appended to buf
-            while (pos < mb && m + 31 <= C) {
-                const int e = pos + lane;
-                const bool valid = e < mb;
-                unsigned v = 0;
-                int x = 0, H = 0;
-                if (valid) load_cand(L, e, Y0, k, Y, v, x, H);
-                const RoundStep st = round_step(valid, x, H, lane, n, carry0);
-                const unsigned bal = __ballot_sync(0xffffffffu, st.keep);
-                if (st.keep) buf[m + __popc(bal & lt)] = v;
-                m += __popc(bal);
-                pos += 31;
+            while (pos < mb && m + 62 <= C) {
+                const int ea = pos + lane, eb = pos + 31 + lane;
+                const bool va = ea < mb, vb = eb < mb;
+                unsigned v0 = 0, v1 = 0;
+                int x0 = 0, H0 = 0, x1 = 0, H1 = 0;
+                load_cand(L, min(ea, mb - 1), Y0, k, Y, v0, x0, H0);  // clamped index: no branch, result unused if !va
+                load_cand(L, min(eb, mb - 1), Y0, k, Y, v1, x1, H1);
+                const bool ka = chunk_round<GS0>(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0);
+                const bool kb = chunk_round<GS0>(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0);
+                const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
+                if (ka) buf[m + __popc(ba & lt)] = v0;
+                m += __popc(ba);
+                if (kb) buf[m + __popc(bb & lt)] = v1;
+                m += __popc(bb);
+                pos += 62;
             }
             __syncwarp();
+            PROF_ADD(2); PROF_CNT(10, m); PROF_CNT(11, 1);
             // rounds over buf until nothing is dropped
             for (;;) {
-                int wp = 0, carryB = -1, total_owned = 0;
-                for (int base = 0; base < m; base += 31) {
-                    const int e = base + lane;
-                    const bool valid = e < m;
-                    const unsigned v = valid ? buf[e] : 0u;
-                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y, H = x * x + g * g;
-                    const RoundStep st = round_step(valid, x, H, lane, n, carryB);
-                    const unsigned bal = __ballot_sync(0xffffffffu, st.keep);
+                int wp = 0, carryB = -1;
+                for (int base = 0; base < m; base += 62) {
+                    const int ea = base + lane, eb = base + 31 + lane;
+                    const bool va = ea < m, vb = eb < m;
+                    const unsigned v0 = va ? buf[ea] : 0u, v1 = vb ? buf[eb] : 0u;
+                    const int x0 = (int)(v0 & 0xffffu), g0 = (int)(v0 >> 16) - Y, H0 = x0 * x0 + g0 * g0;
+                    const int x1 = (int)(v1 & 0xffffu), g1 = (int)(v1 >> 16) - Y, H1 = x1 * x1 + g1 * g1;
+                    const bool ka = chunk_round<GS1>(va, ea + 1 < m, v0, x0, H0, Y, lane, n, carryB);
+                    const bool kb = chunk_round<GS1>(vb, eb + 1 < m, v1, x1, H1, Y, lane, n, carryB);
+                    const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
                     __syncwarp();
-                    if (st.keep) buf[wp + __popc(bal & lt)] = v;
-                    wp += __popc(bal);
-                    total_owned += min(31, m - base);
+                    if (ka) buf[wp + __popc(ba & lt)] = v0;
+                    wp += __popc(ba);
+                    if (kb) buf[wp + __popc(bb & lt)] = v1;
+                    wp += __popc(bb);
                 }
                 __syncwarp();
                 const bool removed = wp != m;
+                PROF_CNT(12, (m + 30) / 31);   // round steps
+                PROF_CNT(13, 1);               // passes
                 m = wp;
                 if (!removed) break;
-                (void)total_owned;
             }
+            PROF_ADD(3);   // rounds
             if (pos >= mb) break;
-            if (m + 31 > C) { overflow = true; break; }  // the envelope itself does not fit
+            if (m + 62 > C) { overflow = true; break; }  // the envelope itself does not fit
         }
         if (overflow) {
             if (lane == 0) ovf_rows[atomicAdd(&ctl->ovf, 1)] = r;
@@ -278,39 +334,58 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
         int carryB = -1;
         double2 carryP = make_double2(0, 0);
         double carryXX = 0;
-        for (int base = 0; base < m; base += 31) {
-            const int e = base + lane;
-            const bool valid = e < m;
-            const unsigned v = valid ? buf[e] : 0u;
-            const int x = (int)(v & 0xffffu), c = (int)(v >> 16), g = c - Y, H = x * x + g * g;
-            const RoundStep st = round_step(valid, x, H, lane, n, carryB);
-            if (st.owned) out[e] = make_int2((int)v, st.Bc + 1);
+        for (int base = 0; base < m; base += 62) {
+            int ee[2] = {base + lane, base + 31 + lane};
+            unsigned vv[2];
+            int xx[2], cc[2], HH[2];
+            RoundStep st[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const bool valid = ee[q] < m;
+                vv[q] = valid ? buf[ee[q]] : 0u;
+                xx[q] = (int)(vv[q] & 0xffffu); cc[q] = (int)(vv[q] >> 16);
+                const int g = cc[q] - Y;
+                HH[q] = xx[q] * xx[q] + g * g;
+                st[q] = round_step(valid, ee[q] + 1 < m, vv[q], xx[q], HH[q], Y, lane, n, carryB);
+                if (st[q].owned) out[ee[q]] = make_int2((int)vv[q], st[q].Bc + 1);
+            }
             if (accumulate) {
-                double2 pb = (st.owned && !(dbg & 8)) ? p2[st.B] : make_double2(1, 1);
-                double xb = (st.owned && want_energy) ? pxx[st.B] : 0;
-                double2 pa;
-                pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1);
-                pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);
-                double xa = __shfl_up_sync(0xffffffffu, xb, 1);
-                if (lane == 0) { pa = carryP; xa = carryXX; }
-                carryP.x = __shfl_sync(0xffffffffu, pb.x, 30);
-                carryP.y = __shfl_sync(0xffffffffu, pb.y, 30);
-                carryXX = __shfl_sync(0xffffffffu, xb, 30);
-                if (st.owned) {
-                    const double W = pb.x - pa.x, X = pb.y - pa.y;
-                    const int id = (dbg & 4) ? (e + 37 * r) % Kcap : idmap[(size_t)c * n + x];
-                    double *a = acc + 4 * (size_t)id;
-                    if (!(dbg & 2)) {
-                        atomicAdd(a, W);
-                        atomicAdd(a + 1, X);
-                        atomicAdd(a + 2, (double)Y * W);
-                    } else if (W == -1.5) a[3] = X;
-                    if (want_energy) e_loc += (xb - xa) - 2.0 * (double)x * X + (double)(H) * W;
+                double2 pb[2];
+                double xb[2];
+                int id[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {  // all loads of both chunks first
+                    pb[q] = (st[q].owned && !(dbg & 8)) ? p2[st[q].B] : make_double2(1, 1);
+                    xb[q] = (st[q].owned && want_energy) ? pxx[st[q].B] : 0;
+                    id[q] = st[q].owned ? ((dbg & 4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double2 pa;
+                    pa.x = __shfl_up_sync(0xffffffffu, pb[q].x, 1);
+                    pa.y = __shfl_up_sync(0xffffffffu, pb[q].y, 1);
+                    double xa = __shfl_up_sync(0xffffffffu, xb[q], 1);
+                    if (lane == 0) { pa = carryP; xa = carryXX; }
+                    carryP.x = __shfl_sync(0xffffffffu, pb[q].x, 30);
+                    carryP.y = __shfl_sync(0xffffffffu, pb[q].y, 30);
+                    carryXX = __shfl_sync(0xffffffffu, xb[q], 30);
+                    if (st[q].owned) {
+                        const double W = pb[q].x - pa.x, X = pb[q].y - pa.y;
+                        double *a = acc + 4 * (size_t)id[q];
+                        if (!(dbg & 2)) {
+                            atomicAdd(a, W);
+                            atomicAdd(a + 1, X);
+                            atomicAdd(a + 2, (double)Y * W);
+                        } else if (W == -1.5) a[3] = X;
+                        if (want_energy) e_loc += (xb[q] - xa) - 2.0 * (double)xx[q] * X + (double)(HH[q]) * W;
+                    }
                 }
             }
         }
         if (lane == 0) rle_cnt[r] = m;
         __syncwarp();
+        PROF_ADD(5);   // output + accumulate
+        PROF_CNT(14, m);
     }
     if (accumulate && want_energy) {
         e_loc = warp_sum(e_loc);
@@ -320,11 +395,21 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
 
 #define BAND_RPW 2
 #define BAND_C 1024
+#ifndef BAND_GS0
+#define BAND_GS0 0   // in-chunk Gauss-Seidel sweeps allowed in round 0 (band list)
+#endif
+#ifndef BAND_GS1
+#define BAND_GS1 0   // ... and in the later rounds.  Measured on a B200 (8192^2, C3): sweeps cut the passes per row
+                      // from 8.3 to 2.6-3.2 but add serial latency; (0,0) 253 us, (0,8) 257, (1,4) 253, (2,4) 278, (3,8) 295.
+#endif
 
 static int band_cap(int n) {
-    // measured on C3-like inputs (DESIGN.md §band kernel): band list <= ~0.28 n
+    // Band-list capacity.  Measured on C3-like inputs: band list <= ~0.28 n entries.
+    //   n <=  8192: 2816 entries -> 4 CTAs/SM (22 KB list + 1 KB masks + 32 KB element buffers + static/system)
+    //   n <= 16384: 6144 entries -> 2 CTAs/SM;   n <= 32768: 12288 entries -> 1 CTA/SM
     int cl = (3 * n) / 8;
-    if (cl > 2816) cl = 2816;  // 4 CTAs/SM: 4 x (22 KB list + 1 KB masks + 32 KB element buffers + static/system)
+    const int cap = n <= 8192 ? 2816 : n <= 16384 ? 6144 : 12288;
+    if (cl > cap) cl = cap;
     if (cl < 512) cl = 512;
     return cl;
 }
@@ -334,7 +419,7 @@ static size_t band_smem(int n, int CL) {
 }
 
 cudaError_t srm_band_setup(int n) {
-    return cudaFuncSetAttribute(k_band<BAND_RPW, BAND_C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    return cudaFuncSetAttribute(k_band<BAND_RPW, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)band_smem(n, band_cap(n)));
 }
 
@@ -344,7 +429,7 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
                             int dbg) {
     const int CL = band_cap(g.n);
     const int R = BAND_NW * BAND_RPW;
-    k_band<BAND_RPW, BAND_C><<<g.nrows() / R, BAND_NT, band_smem(g.n, CL), st>>>(
+    k_band<BAND_RPW, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / R, BAND_NT, band_smem(g.n, CL), st>>>(
         bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
         respect_stop, dbg);
     return cudaGetLastError();

@@ -22,6 +22,7 @@ struct SrmCtl {
     float E;        // Energy (float like the reference)
     int ovf;        // rows handed to the robust path by the band kernel (this labelling)
     int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
+    unsigned long long prof[16];  // optional per-phase clock / element counters of the band kernel (dbg & 1)
 };
 
 __host__ __device__ __forceinline__ int srm_pack(int x, int y) { return (x & 0xffff) | (y << 16); }

@@ -141,14 +141,25 @@ void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, s
 #define ROW_NT 128
 #define ROW_NW (ROW_NT / 32)
 
-__device__ __forceinline__ int min8_dist(uint4 v, int Y, int *g, short *cs) {
-    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+// Column candidates c(x,Y) of 8 consecutive columns for row Y (word-row j, bit k), straight from the bitmap and
+// the carries (semantics of gcvt.cu:77-216); returns the minimum |c - Y| (SRM_BIG for a column without sites).
+__device__ __forceinline__ int cand8_dist(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                          const short *__restrict__ dn, size_t o, int j, int k, int Y, int *g, short *cs) {
+    const uint4 w0 = *reinterpret_cast<const uint4 *>(bits + o), w1 = *reinterpret_cast<const uint4 *>(bits + o + 4);
+    const uint4 u4 = *reinterpret_cast<const uint4 *>(up + o), d4 = *reinterpret_cast<const uint4 *>(dn + o);
+    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
     int M = SRM_BIG;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        short c = (short)((wv[k >> 1] >> ((k & 1) * 16)) & 0xffff);
-        int d = (c == SRM_MARK) ? SRM_BIG : abs((int)c - Y);
-        if (cs) { cs[k] = c; g[k] = d; }
+    for (int q = 0; q < 8; ++q) {
+        const int u0 = (short)((uu[q >> 1] >> ((q & 1) * 16)) & 0xffff), d0 = (short)((dd[q >> 1] >> ((q & 1) * 16)) & 0xffff);
+        const uint32_t mlo = w[q] & (0xffffffffu >> (31 - k));
+        const uint32_t mhi = (k == 31) ? 0u : (w[q] & (0xffffffffu << (k + 1)));
+        const int U = mlo ? 32 * j + 31 - __clz(mlo) : u0;
+        const int D = mhi ? 32 * j + __ffs(mhi) - 1 : d0;
+        const int c = srm_choose_col(U, D, Y);
+        const int d = (c == SRM_MARK) ? SRM_BIG : abs(c - Y);
+        if (cs) { cs[q] = (short)c; g[q] = d; }
         M = min(M, d);
     }
     return M;
@@ -169,8 +180,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
     __shared__ int wtot[ROW_NW];
     if (respect_stop && ctl->stop) return;
     EnvSmem s;
-    short *cyrow = (short *)smem_raw;  // column candidates of the row
-    s.x = (unsigned short *)(cyrow + n);
+    s.x = (unsigned short *)smem_raw;
     s.c = (short *)(s.x + n);
     s.S = s.c + n;
     s.sb = sb_;
@@ -179,20 +189,8 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
     const int total = rows ? *count : nrows;
     for (int q = blockIdx.x; q < total; q += gridDim.x) {
         const int r = rows ? rows[q] : q, Y = row0 + r;
-        {   // column pass of this row (semantics of gcvt.cu:77-216): nearest site above / below from the bitmap
-            const int j = Y >> 5, k = Y & 31;
-            for (int x = t; x < n; x += ROW_NT) {
-                const size_t o = (size_t)j * n + x;
-                const uint32_t wd = bits[o];
-                const uint32_t mlo = wd & (0xffffffffu >> (31 - k));
-                const uint32_t mhi = (k == 31) ? 0u : (wd & (0xffffffffu << (k + 1)));
-                const int U = mlo ? 32 * j + 31 - __clz(mlo) : (int)up[o];
-                const int D = mhi ? 32 * j + __ffs(mhi) - 1 : (int)dn[o];
-                cyrow[x] = (short)srm_choose_col(U, D, Y);
-            }
-        }
-        __syncthreads();
-        const short *row = cyrow;
+        const int j = Y >> 5, kbit = Y & 31;
+        const size_t wrow = (size_t)j * n;
         const int nchunks = n >> 8;
         const int c0 = (w * nchunks) / ROW_NW, c1 = ((w + 1) * nchunks) / ROW_NW;
         const int rb = c0 << 8;
@@ -202,18 +200,17 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
             const int x0 = (c << 8) + lane * 8;
             int g[8];
             short cs[8];
-            uint4 v = *reinterpret_cast<const uint4 *>(row + x0);
-            int M = min8_dist(v, Y, g, cs);
+            int M = cand8_dist(bits, up, dn, wrow + x0, j, kbit, Y, g, cs);
             int ML = __shfl_up_sync(0xffffffffu, M, 1), MR = __shfl_down_sync(0xffffffffu, M, 1);
             if (lane == 0) {
                 if (c == c0) {
                     ML = SRM_BIG;
-                    if (x0 > 0) ML = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 - 8), Y, nullptr, nullptr);
+                    if (x0 > 0) ML = cand8_dist(bits, up, dn, wrow + x0 - 8, j, kbit, Y, nullptr, nullptr);
                 } else ML = carryM;
             }
             if (lane == 31) {
                 MR = SRM_BIG;
-                if (x0 + 8 < n) MR = min8_dist(*reinterpret_cast<const uint4 *>(row + x0 + 8), Y, nullptr, nullptr);
+                if (x0 + 8 < n) MR = cand8_dist(bits, up, dn, wrow + x0 + 8, j, kbit, Y, nullptr, nullptr);
             }
             carryM = __shfl_sync(0xffffffffu, M, 31);
             const int TL = ML * ML + 225, TR = MR * MR + 225;  // 15^2: farthest column of an adjacent block
@@ -274,7 +271,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
     }
 }
 
-static size_t row_smem_bytes(int n) { return (size_t)n * 8; }
+static size_t row_smem_bytes(int n) { return (size_t)n * 6; }  // 192 KB at n = 32768
 
 cudaError_t srm_label_setup(int n) {
     cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(n));
