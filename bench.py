@@ -146,6 +146,8 @@ def run_ours(args):
     eng = CudaBandEngine(n, r0, r1, local)
     eng.set_inputs(dens, mask, vor)
     sl = ShardedLloyd(n, rank, world, eng, dist if world > 1 else None)
+    if world > 1 and not args.py_collective:
+        sl.bind_native_collective()   # NCCL all-reduce issued by libsrm inside its C++ loop
 
     def barrier():
         torch.cuda.synchronize()
@@ -207,6 +209,8 @@ def run_ours(args):
         eng2 = CudaBandEngine(n, r0, r1, local)
         eng2.set_inputs(dens, mask, vor)
         sl2 = ShardedLloyd(n, rank, world, eng2, dist)
+        if not args.py_collective:
+            sl2.bind_native_collective()
         sl2.run(e2e_iters)
         lab = sl2.final_labels()
         torch.cuda.synchronize()
@@ -326,6 +330,8 @@ def main():
     ap.add_argument("--e2e-iters", dest="e2e_iters", type=int, default=100)
     ap.add_argument("--cpu-iters", dest="cpu_iters", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--py-collective", dest="py_collective", action="store_true",
+                    help="N>1: all-reduce through torch.distributed per step instead of libsrm's own NCCL loop")
     ap.add_argument("--_ref_child", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

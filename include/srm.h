@@ -107,12 +107,18 @@ int srm_label_accumulate(srm_ctx *ctx, int want_energy); /* srm_label + srm_accu
  * 4*capacity+4 doubles: (W, X, Y, 0) per site, then (energy_sum,0,0,0). */
 int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
 
+/* Row bands on several GPUs: rank 0 obtains a 128-byte id, the caller distributes it, every rank binds its band
+ * context; srm_iterate / srm_run then all-reduce (NCCL, sum, fp64) the accumulators between the band kernel and the
+ * update, on the context's stream.  NCCL is loaded at run time (libnccl.so.2, or $SRM_NCCL_LIB). */
+int srm_nccl_unique_id(char *id128);
+int srm_nccl_init(srm_ctx *ctx, const char *id128, int rank, int world);
+
 /* iters x (label, accumulate, update) with the reference's energy/omega schedule; stop_rule != 0
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */
 int srm_iterate(srm_ctx *ctx, int iters, int stop_rule);
 /* Same loop with CUDA events between the stages (measurement only): stage_ms[6] receives the summed device
- * milliseconds of {site bitmap + carries, fused band kernel, robust row path, (unused), update + control,
- * whole iteration}. */
+ * milliseconds of {site bitmap + carries, fused band kernel, robust row path, accumulator all-reduce (row bands),
+ * update + control, whole iteration}. */
 int srm_iterate_profiled(srm_ctx *ctx, int iters, int stop_rule, float *stage_ms);
 /* Whole gCVT on resident inputs: loop + final labelling. */
 int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);

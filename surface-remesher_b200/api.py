@@ -52,6 +52,8 @@ def lib():
     L.srm_create.argtypes = [C.POINTER(p), i, i, i, i]
     L.srm_destroy.argtypes = [p]
     L.srm_set_stream.argtypes = [p, p]
+    L.srm_nccl_unique_id.argtypes = [p]
+    L.srm_nccl_init.argtypes = [p, p, i, i]
     L.srm_synchronize.argtypes = [p]
     L.srm_set_density.argtypes = [p, p, i]
     L.srm_set_mask.argtypes = [p, p, i]
@@ -73,7 +75,7 @@ def lib():
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
-                 "srm_set_stream", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
+                 "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
@@ -205,6 +207,15 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         _ck(lib().srm_set_stream(self._h, C.c_void_p(int(cuda_stream_ptr))))
 
+    @staticmethod
+    def nccl_unique_id():
+        buf = C.create_string_buffer(128)
+        _ck(lib().srm_nccl_unique_id(buf))
+        return buf.raw
+
+    def nccl_init(self, id128, rank, world):
+        _ck(lib().srm_nccl_init(self._h, C.create_string_buffer(bytes(id128), 128), int(rank), int(world)))
+
     def synchronize(self):
         _ck(lib().srm_synchronize(self._h))
 
@@ -263,7 +274,7 @@ class Context:
     def iterate(self, iters, stop_rule=False):
         _ck(lib().srm_iterate(self._h, int(iters), int(bool(stop_rule))))
 
-    STAGES = ("bitmap+carry", "band_fused", "robust_rows", "unused", "update", "iteration")
+    STAGES = ("bitmap+carry", "band_fused", "robust_rows", "allreduce", "update", "iteration")
 
     def iterate_profiled(self, iters, stop_rule=False):
         """dict stage -> summed device ms over `iters` iterations (CUDA events between the stages)."""

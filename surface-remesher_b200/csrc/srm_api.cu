@@ -15,6 +15,7 @@
 #include <string.h>
 #include <time.h>
 #include <algorithm>
+#include <dlfcn.h>
 #include <mutex>
 #include <vector>
 
@@ -38,6 +39,39 @@ static int fail(int code, const char *fmt, ...) {
 
 extern "C" const char *srm_last_error(void) { return g_err; }
 extern "C" int srm_version(void) { return 100; }
+
+// ---- NCCL, bound at run time (dlopen) so that libsrm.so has no link-time dependency on it.  Only the row-band
+// all-reduce uses it; single-GPU use never loads it.
+typedef struct { char internal[128]; } SrmNcclId;
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(SrmNcclId *) = nullptr;
+    int (*CommInitRank)(void **, int, SrmNcclId, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+
+static int load_nccl() {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.handle) return SRM_OK;
+    const char *names[] = {getenv("SRM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names)
+        if (nm && (h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return fail(SRM_ERR_CUDA, "NCCL library not found (libnccl.so.2; set SRM_NCCL_LIB): %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(SrmNcclId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, SrmNcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(SRM_ERR_CUDA, "NCCL library lacks a required symbol");
+    g_nccl.handle = h;
+    return SRM_OK;
+}
 
 struct srm_ctx {
     SrmGrid g{};
@@ -69,6 +103,8 @@ struct srm_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
     bool stopped = false;
+    void *comm = nullptr;  // NCCL communicator of the row bands (world > 1)
+    int world = 1;
 };
 
 static int valid_n(int n) { return n >= 256 && n <= 32768 && (n % 256) == 0; }
@@ -159,6 +195,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (!c) return SRM_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
                     c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
                     c->scratch_map, c->ctl};
@@ -167,6 +204,40 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
+    return SRM_OK;
+}
+
+// Row-band collective: one all-reduce (sum, fp64) of the per-site accumulators per iteration.
+// rank 0 creates the id, the caller distributes the 128 bytes (torch.distributed / MPI / files: plumbing),
+// every rank calls srm_nccl_init on its band context.
+extern "C" int srm_nccl_unique_id(char *id128) {
+    if (!id128) return fail(SRM_ERR_ARG, "srm_nccl_unique_id: null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    SrmNcclId id;
+    int e = g_nccl.GetUniqueId(&id);
+    if (e) return fail(SRM_ERR_CUDA, "ncclGetUniqueId: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
+    memcpy(id128, id.internal, 128);
+    return SRM_OK;
+}
+
+extern "C" int srm_nccl_init(srm_ctx *c, const char *id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(SRM_ERR_ARG, "srm_nccl_init: bad argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    SrmNcclId id;
+    memcpy(id.internal, id128, 128);
+    int e = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (e) { c->comm = nullptr; return fail(SRM_ERR_CUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error"); }
+    c->world = world;
+    return SRM_OK;
+}
+
+static int allreduce_acc(srm_ctx *c) {
+    if (!c->comm) return SRM_OK;
+    int e = g_nccl.AllReduce(c->acc, c->acc, 4 * (size_t)c->Kcap + 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
+    if (e) return fail(SRM_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
     return SRM_OK;
 }
 
@@ -424,6 +495,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
         const int buf = it & 1, want_energy = (it % 10) == 0;
         rc = label_with(c, buf, 1, 1, want_energy);
         if (rc) return rc;
+        rc = allreduce_acc(c);  // no-op for a single band
+        if (rc) return rc;
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
                           c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
                           stop_rule, 1);
@@ -440,8 +513,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
 }
 
 // Same loop as srm_iterate with CUDA events between the stages; stage_ms[6] receives the summed device
-// time of {site bitmap + carries, fused band kernel, robust row path, (unused), update + control,
-// whole iteration}.
+// time of {site bitmap + carries, fused band kernel, robust row path, accumulator all-reduce (row bands),
+// update + control, whole iteration}.
 extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float *stage_ms) {
     int rc = require_ready(c, "srm_iterate_profiled", true);
     if (rc) return rc;
@@ -470,6 +543,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
                           c->acc, c->Kcap, c->ctl, 1, want_energy, 1));
         CK(cudaEventRecord(e[3], c->stream));
+        rc = allreduce_acc(c);
+        if (rc) return rc;
         CK(cudaEventRecord(e[4], c->stream));
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
                           c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,

@@ -101,7 +101,28 @@ class ShardedLloyd:
         self.engine.update()
         self.it += 1
 
+    def bind_native_collective(self):
+        """world > 1 with the CUDA engine: hand the all-reduce to libsrm itself (NCCL communicator created from an id
+        broadcast through torch.distributed), so that run() is one C++ loop without per-iteration Python."""
+        if self.world == 1 or not hasattr(self.engine, "ctx"):
+            return False
+        import torch
+        dev = self.engine.device
+        if self.rank == 0:
+            raw = self.engine.ctx.nccl_unique_id()
+            t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)
+        else:
+            t = torch.zeros(128, dtype=torch.uint8, device=dev)
+        self.dist.broadcast(t, 0)
+        self.engine.ctx.nccl_init(bytes(t.cpu().tolist()), self.rank, self.world)
+        self.native = True
+        return True
+
     def run(self, iters):
+        if getattr(self, "native", False) or (self.world == 1 and hasattr(self.engine, "ctx")):
+            self.engine.ctx.iterate(iters, stop_rule=False)   # fused band kernel (+ NCCL all-reduce) + update, in C++
+            self.it += iters
+            return
         for _ in range(iters):
             self.step()
 
