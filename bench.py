@@ -66,11 +66,24 @@ def make_inputs(n, k, pinned):
         return np.empty(shape, dtype)
 
     dens = alloc((n, n), np.float32)
-    step = 512
-    for r0 in range(0, n, step):
-        dens[r0:r0 + step] = I.density_c3(n, rows=(r0, min(n, r0 + step)))
     mask = alloc((n, n), np.uint8)
-    mask[:] = I.mask_c3(dens)
+    use_gpu = False
+    try:
+        import torch
+        use_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    if use_gpu:   # same formulas evaluated on the GPU (seconds instead of a minute at 32768^2)
+        import torch
+        d_t, m_t = I.c3_torch(n, torch.device("cuda", torch.cuda.current_device()))
+        dens[:] = d_t.cpu().numpy(); mask[:] = m_t.cpu().numpy()
+        del d_t, m_t
+        torch.cuda.empty_cache()
+    else:
+        step = 512
+        for r0 in range(0, n, step):
+            dens[r0:r0 + step] = I.density_c3(n, rows=(r0, min(n, r0 + step)))
+        mask[:] = I.mask_c3(dens)
     vor = alloc((n, n, 2), np.int16)
     S.api._ck(S.lib().srm_seed(vor.ctypes.data, dens.ctypes.data, mask.ctypes.data, int(k), n, None))
     log(f"[bench] inputs n={n} sites={k}+{int(mask.sum())} mask in {time.time() - t0:.1f}s")
@@ -176,8 +189,8 @@ def run_ours(args):
 
     # ---- per-stage pass (same loop, events between the stages) for the roofline object; N=1 only
     stage = None
-    if world == 1:
-        stage = eng.ctx.iterate_profiled(K, stop_rule=False)
+    if world == 1 or not args.py_collective:
+        stage = eng.ctx.iterate_profiled(K, stop_rule=False)   # every rank takes part in the all-reduce
         torch.cuda.synchronize()
         runs, ovf = eng.ctx.debug_counts()
 
@@ -204,13 +217,13 @@ def run_ours(args):
     else:
         # each rank: upload its inputs, run the loop, download its band of labels
         eng.close()
-        barrier()
-        t0 = time.perf_counter()
-        eng2 = CudaBandEngine(n, r0, r1, local)
-        eng2.set_inputs(dens, mask, vor)
+        eng2 = CudaBandEngine(n, r0, r1, local)   # context + communicator are set-up, like the process group
         sl2 = ShardedLloyd(n, rank, world, eng2, dist)
         if not args.py_collective:
             sl2.bind_native_collective()
+        barrier()
+        t0 = time.perf_counter()
+        eng2.set_inputs(dens, mask, vor)
         sl2.run(e2e_iters)
         lab = sl2.final_labels()
         torch.cuda.synchronize()
@@ -244,7 +257,9 @@ def run_ours(args):
         "gpu_launches": 6 * K * world,  # k_bits, k_carry, k_band, k_row, k_update_pos, k_update_resolve per step and rank
         "clocks": clocks,
     }
-    if stage is not None:
+    if stage is not None and world > 1:
+        line["config"]["stages_ms_per_step_rank0"] = {s: v / K for s, v in stage.items()}
+    if stage is not None and world == 1:
         row_ms = stage["band_fused"] / K
         # algorithmic bytes of one k_band launch: per 16-row band and column 8 B (bitmap word + up/dn carries)
         # = N/2; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B

@@ -1,10 +1,10 @@
-// srm_band.cu — fused band kernel: exact labelling of R = 16 consecutive rows straight from the
+// srm_band.cu — fused band kernel: exact labelling of R = 8 (or 16) consecutive rows straight from the
 // column bitmap, run-length output and (optionally) the per-site centroid/energy accumulation, in
 // one launch.  This is the hot kernel of the Lloyd loop; it replaces the reference's pba2DCompute +
 // pbaCVDComputeCentroid (+ pbaCVDCalcEnergy) chain (gcvt.cu:921-978, 1008-1023, 1059-1083: ~15
 // launches, ~75 B/px) and never materialises a per-pixel array.
 //
-// One CTA = 8 warps = one band of R = 8*RPW rows.
+// One CTA = 8 warps = one band of R = 8*RPW rows (RPW = 1 by default: 8-row bands).
 //   Phase A (whole CTA, once per band): per column, from the bitmap word and the up/dn carries, the
 //     nearest site row above the band (U), below it (D) and the in-band bits.  Columns that are
 //     dominated for EVERY row of the band by both neighbouring 8-column blocks are dropped
@@ -24,6 +24,7 @@
 // robust path (k_row in srm_label.cu).
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
+#include <stdlib.h>
 
 #define BAND_NT 256
 #define BAND_NW 8
@@ -393,7 +394,6 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
     }
 }
 
-#define BAND_RPW 2
 #define BAND_C 1024
 #ifndef BAND_GS0
 #define BAND_GS0 0   // in-chunk Gauss-Seidel sweeps allowed in round 0 (band list)
@@ -419,8 +419,21 @@ static size_t band_smem(int n, int CL) {
 }
 
 cudaError_t srm_band_setup(int n) {
-    return cudaFuncSetAttribute(k_band<BAND_RPW, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)band_smem(n, band_cap(n)));
+    const int smem = (int)band_smem(n, band_cap(n));
+    cudaError_t e = cudaFuncSetAttribute(k_band<1, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_band<2, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+}
+
+// Band height: 8 rows (one row per warp) or 16 rows (two rows per warp, Phase A amortised over twice the rows).
+// Measured on a B200 (C3): 8192^2: 231 us vs 253 us, 4096^2: 61 vs 81 us, 8192^2 on 2 GPUs: 16-row bands leave 256
+// CTAs for 592 CTA slots.  8-row bands prune harder (bounds gmax <= gmin + 7) and give twice the CTAs, which matters
+// more than Phase A for a latency-bound kernel; 16 stays selectable for experiments (SRM_BAND_RPW=2).
+static int band_rpw(int nrows) {
+    (void)nrows;
+    const char *env = getenv("SRM_BAND_RPW");
+    if (env && (env[0] == '1' || env[0] == '2')) return env[0] - '0';
+    return 1;
 }
 
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
@@ -428,9 +441,14 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
                             double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
                             int dbg) {
     const int CL = band_cap(g.n);
-    const int R = BAND_NW * BAND_RPW;
-    k_band<BAND_RPW, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / R, BAND_NT, band_smem(g.n, CL), st>>>(
-        bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
-        respect_stop, dbg);
+    const size_t smem = band_smem(g.n, CL);
+    if (band_rpw(g.nrows()) == 2)
+        k_band<2, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / 16, BAND_NT, smem, st>>>(
+            bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
+            respect_stop, dbg);
+    else
+        k_band<1, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / 8, BAND_NT, smem, st>>>(
+            bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
+            respect_stop, dbg);
     return cudaGetLastError();
 }

@@ -52,6 +52,46 @@ def density_c3(n, seed=42, rows=None):
     return np.where(inside, w, 0.0).astype(np.float32)
 
 
+def c3_torch(n, device, seed=42, every=16):
+    """density_c3 + mask_c3 evaluated with torch on `device` (same formulas, float64 math, band by band).
+    Used by bench.py / tools for large grids; values agree with the numpy generator to the last ulp of exp()."""
+    import torch
+    with np.errstate(over="ignore"):
+        g = splitmix64(seed)
+        ridges = []
+        for _ in range(16):
+            cx, cy = 0.1 + 0.8 * next(g), 0.1 + 0.8 * next(g)
+            th = 2 * np.pi * next(g)
+            s1, s2 = 0.15 + 0.25 * next(g), 0.005 + 0.015 * next(g)
+            a = 5 + 45 * next(g)
+            ridges.append((cx, cy, th, s1, s2, a))
+    dens = torch.empty((n, n), dtype=torch.float32, device=device)
+    xs = (torch.arange(n, dtype=torch.float64, device=device) / (n - 1))[None, :]
+    step = max(64, min(n, (1 << 24) // n))
+    for r0 in range(0, n, step):
+        r1 = min(n, r0 + step)
+        ys = (torch.arange(r0, r1, dtype=torch.float64, device=device) / (n - 1))[:, None]
+        kappa = torch.zeros((r1 - r0, n), dtype=torch.float64, device=device)
+        for cx, cy, th, s1, s2, a in ridges:
+            dx, dy = xs - cx, ys - cy
+            e1 = dx * np.cos(th) + dy * np.sin(th)
+            e2 = -dx * np.sin(th) + dy * np.cos(th)
+            kappa += a * torch.exp(-0.5 * ((e1 / s1) ** 2 + (e2 / s2) ** 2))
+        w = torch.clamp(0.01 + kappa, 1e-3, 50.0)
+        dx, dy = xs - 0.5, ys - 0.5
+        rr = torch.sqrt(dx * dx + dy * dy)
+        phi = torch.atan2(dy, dx)
+        inside = rr < 0.45 * (1 + 0.15 * torch.cos(5 * phi))
+        dens[r0:r1] = torch.where(inside, w, torch.zeros_like(w)).to(torch.float32)
+    ins = dens != 0
+    edge = ins.clone()
+    edge[1:-1, 1:-1] = ins[1:-1, 1:-1] & ~(ins[:-2, 1:-1] & ins[2:, 1:-1] & ins[1:-1, :-2] & ins[1:-1, 2:])
+    idx = torch.nonzero(edge.reshape(-1), as_tuple=False).reshape(-1)[::every]   # scan order, like np.nonzero
+    mask = torch.zeros(n * n, dtype=torch.uint8, device=device)
+    mask[idx] = 1
+    return dens, mask.reshape(n, n)
+
+
 def mask_c3(density, every=16):
     """Boundary samples of the non-zero domain, one every `every` boundary pixels in scan order
     (mimics generateMask on the mesh border vertices)."""
