@@ -394,7 +394,6 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
     }
 }
 
-#define BAND_C 1024
 #ifndef BAND_GS0
 #define BAND_GS0 0   // in-chunk Gauss-Seidel sweeps allowed in round 0 (band list)
 #endif
@@ -402,6 +401,10 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
 #define BAND_GS1 0   // ... and in the later rounds.  Measured on a B200 (8192^2, C3): sweeps cut the passes per row
                       // from 8.3 to 2.6-3.2 but add serial latency; (0,0) 253 us, (0,8) 257, (1,4) 253, (2,4) 278, (3,8) 295.
 #endif
+
+// Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62.  Rows of an n-wide grid with the
+// BASELINE site densities have ~n/26 runs (316 at 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
+static int band_bufcap(int n) { return n <= 8192 ? 1024 : n <= 16384 ? 1536 : 3072; }
 
 static int band_cap(int n) {
     // Band-list capacity.  Measured on C3-like inputs: band list <= ~0.28 n entries.
@@ -415,14 +418,23 @@ static int band_cap(int n) {
 }
 
 static size_t band_smem(int n, int CL) {
-    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * BAND_C * 4;
+    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4;
+}
+
+template <int RPW, int C>
+static cudaError_t band_setup_one(int smem) {
+    return cudaFuncSetAttribute(k_band<RPW, C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t srm_band_setup(int n) {
     const int smem = (int)band_smem(n, band_cap(n));
-    cudaError_t e = cudaFuncSetAttribute(k_band<1, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_band<2, BAND_C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e;
+    switch (band_bufcap(n)) {
+        case 1024: e = band_setup_one<1, 1024>(smem); if (e == cudaSuccess) e = band_setup_one<2, 1024>(smem); break;
+        case 1536: e = band_setup_one<1, 1536>(smem); if (e == cudaSuccess) e = band_setup_one<2, 1536>(smem); break;
+        default:   e = band_setup_one<1, 3072>(smem); if (e == cudaSuccess) e = band_setup_one<2, 3072>(smem); break;
+    }
+    return e;
 }
 
 // Band height: 8 rows (one row per warp) or 16 rows (two rows per warp, Phase A amortised over twice the rows).
@@ -436,19 +448,27 @@ static int band_rpw(int nrows) {
     return 1;
 }
 
+template <int RPW, int C>
+static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, const short *up, const short *dn, SrmGrid g,
+                            int CL, int2 *rle, int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX,
+                            const int *idmap, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
+                            int respect_stop, int dbg) {
+    k_band<RPW, C, BAND_GS0, BAND_GS1><<<g.nrows() / (BAND_NW * RPW), BAND_NT, smem, st>>>(
+        bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
+        respect_stop, dbg);
+}
+
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                             int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
                             double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
                             int dbg) {
     const int CL = band_cap(g.n);
     const size_t smem = band_smem(g.n, CL);
-    if (band_rpw(g.nrows()) == 2)
-        k_band<2, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / 16, BAND_NT, smem, st>>>(
-            bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
-            respect_stop, dbg);
-    else
-        k_band<1, BAND_C, BAND_GS0, BAND_GS1><<<g.nrows() / 8, BAND_NT, smem, st>>>(
-            bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
-            respect_stop, dbg);
+    const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
+#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop, dbg
+    if (C == 1024) { if (rpw == 1) band_launch_one<1, 1024>(BAND_ARGS); else band_launch_one<2, 1024>(BAND_ARGS); }
+    else if (C == 1536) { if (rpw == 1) band_launch_one<1, 1536>(BAND_ARGS); else band_launch_one<2, 1536>(BAND_ARGS); }
+    else { if (rpw == 1) band_launch_one<1, 3072>(BAND_ARGS); else band_launch_one<2, 3072>(BAND_ARGS); }
+#undef BAND_ARGS
     return cudaGetLastError();
 }

@@ -189,6 +189,7 @@ def test_full_size_properties(n, k, kind):
         c.label()
         lab = c.get_labels()
         c.accumulate(True)
+        c.synchronize()   # the context runs on its own non-blocking stream: finish k_acc before torch reads the buffer
         ptr, cnt = c.acc_buffer()
         import torch
         from surface_remesher_b200.sharded import _CudaArray
