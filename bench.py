@@ -159,8 +159,8 @@ def run_ours(args):
     eng = CudaBandEngine(n, r0, r1, local)
     eng.set_inputs(dens, mask, vor)
     sl = ShardedLloyd(n, rank, world, eng, dist if world > 1 else None)
-    if world > 1 and not args.py_collective:
-        sl.bind_native_collective()   # NCCL all-reduce issued by libsrm inside its C++ loop
+    if world > 1 and args.collective != "py":
+        sl.bind_native_collective(args.collective)   # all-reduce inside libsrm's C++ loop (peer memory or NCCL)
 
     def barrier():
         torch.cuda.synchronize()
@@ -189,7 +189,7 @@ def run_ours(args):
 
     # ---- per-stage pass (same loop, events between the stages) for the roofline object; N=1 only
     stage = None
-    if world == 1 or not args.py_collective:
+    if world == 1 or args.collective != "py":
         stage = eng.ctx.iterate_profiled(K, stop_rule=False)   # every rank takes part in the all-reduce
         torch.cuda.synchronize()
         runs, ovf = eng.ctx.debug_counts()
@@ -217,13 +217,13 @@ def run_ours(args):
     else:
         # each rank: upload its inputs, run the loop, download its band of labels
         eng.close()
-        eng2 = CudaBandEngine(n, r0, r1, local)   # context + communicator are set-up, like the process group
+        eng2 = CudaBandEngine(n, r0, r1, local)   # the context is set-up, like the process group
         sl2 = ShardedLloyd(n, rank, world, eng2, dist)
-        if not args.py_collective:
-            sl2.bind_native_collective()
         barrier()
         t0 = time.perf_counter()
         eng2.set_inputs(dens, mask, vor)
+        if args.collective != "py":
+            sl2.bind_native_collective(args.collective)   # peer mappings refer to this call's accumulators
         sl2.run(e2e_iters)
         lab = sl2.final_labels()
         torch.cuda.synchronize()
@@ -248,7 +248,7 @@ def run_ours(args):
         "dtype": "int32 labels / f64 accumulators", "data": "synthetic",
         "config": {"workload": f"C3 curvature-like anisotropic density {n}x{n}, {k} sites + {int(mask.sum())} fixed boundary sites "
                                "(BASELINE.json configs[2])", "grid": n, "sites": st["num_sites"],
-                   "parallelism": f"row bands x{world}" if world > 1 else "single GPU",
+                   "parallelism": f"row bands x{world}, collective={args.collective}" if world > 1 else "single GPU",
                    "l2": "fp64 prefix arrays (24 B/px, read at run ends) + site-id map (4 B/px, read per run) "
                          f"= {28 * N / 1e6:.0f} MB > 126 MB L2; no explicit flush",
                    "stop_rule": "off (fixed step count); energy every 10th step like the reference"},
@@ -345,8 +345,9 @@ def main():
     ap.add_argument("--e2e-iters", dest="e2e_iters", type=int, default=100)
     ap.add_argument("--cpu-iters", dest="cpu_iters", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--py-collective", dest="py_collective", action="store_true",
-                    help="N>1: all-reduce through torch.distributed per step instead of libsrm's own NCCL loop")
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl", "py"],
+                    help="N>1: p2p = fused all-reduce over peer memory inside the update kernel (default); nccl = NCCL "
+                         "all-reduce issued by libsrm; py = torch.distributed all-reduce per step from Python")
     ap.add_argument("--_ref_child", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

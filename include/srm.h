@@ -94,6 +94,10 @@ int srm_set_site_map(srm_ctx *ctx, const short *site_map, int on_device);
 int srm_set_sites(srm_ctx *ctx, const int *packed_xy, int num, int on_device);
 int srm_get_sites(srm_ctx *ctx, int *packed_xy_host, int capacity, int *num_out);
 int srm_set_omega(srm_ctx *ctx, float omega);
+/* delaunayInput's site scan (delaunay.h:46-57): free sites (label == self, not a constraint pixel) in x-outer /
+ * y-inner order as points (x*scale + l, y*scale + b).  mask_host may be NULL.  Replaces <- delaunay.h:30-57. */
+int srm_extract_sites(srm_ctx *ctx, const unsigned char *mask_host, double scale, double l, double b,
+                      double *points_xy, int capacity, int *num_out);
 /* Options: "robust_only" = 1 labels every row with the worst-case-capacity row path instead of the fused band
  * kernel (same results; used by the tests to pin that path). */
 int srm_set_option(srm_ctx *ctx, const char *name, int value);
@@ -112,6 +116,13 @@ int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
  * update, on the context's stream.  NCCL is loaded at run time (libnccl.so.2, or $SRM_NCCL_LIB). */
 int srm_nccl_unique_id(char *id128);
 int srm_nccl_init(srm_ctx *ctx, const char *id128, int rank, int world);
+
+/* Alternative to the NCCL all-reduce: a FUSED all-reduce over peer memory.  Every rank describes its accumulator
+ * pair and arrival flags in a 160-byte blob (CUDA IPC handles), the caller gathers the blobs of all ranks, every rank
+ * connects (collective; after the sites are set).  From then on the update kernel itself waits for the peers'
+ * arrival flags and pulls the per-site partial sums from their memory over NVLink; no collective kernel runs. */
+int srm_p2p_info(srm_ctx *ctx, void *blob160);
+int srm_p2p_connect(srm_ctx *ctx, const void *blobs /* world x 160 bytes */, int rank, int world);
 
 /* iters x (label, accumulate, update) with the reference's energy/omega schedule; stop_rule != 0
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */

@@ -54,6 +54,8 @@ def lib():
     L.srm_set_stream.argtypes = [p, p]
     L.srm_nccl_unique_id.argtypes = [p]
     L.srm_nccl_init.argtypes = [p, p, i, i]
+    L.srm_p2p_info.argtypes = [p, p]
+    L.srm_p2p_connect.argtypes = [p, p, i, i]
     L.srm_synchronize.argtypes = [p]
     L.srm_set_density.argtypes = [p, p, i]
     L.srm_set_mask.argtypes = [p, p, i]
@@ -61,6 +63,7 @@ def lib():
     L.srm_set_sites.argtypes = [p, p, i, i]
     L.srm_get_sites.argtypes = [p, p, i, C.POINTER(i)]
     L.srm_set_omega.argtypes = [p, C.c_float]
+    L.srm_extract_sites.argtypes = [p, p, d, d, d, p, i, C.POINTER(i)]
     L.srm_set_option.argtypes = [p, C.c_char_p, i]
     L.srm_label.argtypes = [p]
     L.srm_accumulate.argtypes = [p, i]
@@ -75,8 +78,8 @@ def lib():
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
-                 "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
-                 "srm_set_sites", "srm_get_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
+                 "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
+                 "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
     _lib = L
@@ -216,6 +219,16 @@ class Context:
     def nccl_init(self, id128, rank, world):
         _ck(lib().srm_nccl_init(self._h, C.create_string_buffer(bytes(id128), 128), int(rank), int(world)))
 
+    def p2p_info(self):
+        buf = C.create_string_buffer(160)
+        _ck(lib().srm_p2p_info(self._h, buf))
+        return buf.raw
+
+    def p2p_connect(self, blobs, rank, world):
+        raw = b"".join(blobs)
+        assert len(raw) == 160 * world
+        _ck(lib().srm_p2p_connect(self._h, C.create_string_buffer(raw, len(raw)), int(rank), int(world)))
+
     def synchronize(self):
         _ck(lib().srm_synchronize(self._h))
 
@@ -246,6 +259,19 @@ class Context:
         out = np.empty(k.value, np.int32)
         _ck(lib().srm_get_sites(self._h, out.ctypes.data_as(C.c_void_p), k.value, C.byref(k)))
         return out[: k.value]
+
+    def extract_sites(self, mask=None, scale=1.0, l=0.0, b=0.0):
+        """Free sites as (M,2) float64 points in delaunayInput's scan order (delaunay.h:46-57)."""
+        k = C.c_int()
+        mp = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, np.uint8)
+            mp = m.ctypes.data_as(C.c_void_p)
+        _ck(lib().srm_extract_sites(self._h, mp, float(scale), float(l), float(b), None, 0, C.byref(k)))
+        out = np.empty((k.value, 2), np.float64)
+        _ck(lib().srm_extract_sites(self._h, mp, float(scale), float(l), float(b), out.ctypes.data_as(C.c_void_p),
+                                    k.value, C.byref(k)))
+        return out
 
     def set_option(self, name, value):
         _ck(lib().srm_set_option(self._h, name.encode(), int(value)))

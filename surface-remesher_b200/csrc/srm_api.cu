@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 #include <algorithm>
 #include <dlfcn.h>
 #include <mutex>
@@ -105,6 +106,14 @@ struct srm_ctx {
     bool stopped = false;
     void *comm = nullptr;  // NCCL communicator of the row bands (world > 1)
     int world = 1;
+    // fused all-reduce over peer memory
+    bool p2p = false;
+    int rank = 0;
+    size_t acc_stride = 0;            // doubles per accumulator buffer (two buffers)
+    int *flags = nullptr;             // arrival flags, one slot per rank
+    const double **d_peer_acc = nullptr;
+    int **d_peer_flags = nullptr;
+    std::vector<void *> ipc_opened;
 };
 
 static int valid_n(int n) { return n >= 256 && n <= 32768 && (n % 256) == 0; }
@@ -118,8 +127,10 @@ static int alloc_sites(srm_ctx *c, int K) {
     CK(cudaMalloc(&c->sites[0], k1 * sizeof(int)));
     CK(cudaMalloc(&c->sites[1], k1 * sizeof(int)));
     CK(cudaMalloc(&c->newpos, k1 * sizeof(int)));
-    CK(cudaMalloc(&c->acc, (4 * (size_t)K + 4) * sizeof(double)));
-    CK(cudaMemsetAsync(c->acc, 0, (4 * (size_t)K + 4) * sizeof(double), c->stream));
+    c->acc_stride = 4 * (size_t)K + 4;  // two buffers: the peer-memory all-reduce alternates them by iteration parity
+    CK(cudaMalloc(&c->acc, 2 * c->acc_stride * sizeof(double)));
+    CK(cudaMemsetAsync(c->acc, 0, 2 * c->acc_stride * sizeof(double), c->stream));
+    c->p2p = false;  // peer mappings refer to the old buffers
     c->cur = 0;
     return SRM_OK;
 }
@@ -178,6 +189,8 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->idmap, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->claim, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
+    CKD(cudaMalloc(&c->flags, 64 * sizeof(int)));
+    CKD(cudaMemsetAsync(c->flags, 0, 64 * sizeof(int), c->stream));
     c->blockcap = c->N / 256 + 2;  // covers both the seed-map compaction (N/1024 tiles) and K <= N sites
     CKD(cudaMalloc(&c->blockcnt, c->blockcap * sizeof(int)));
     CKD(cudaMalloc(&c->blockoff, c->blockcap * sizeof(int)));
@@ -196,6 +209,10 @@ extern "C" int srm_destroy(srm_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    if (c->flags) cudaFree(c->flags);
+    if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
+    if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
                     c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
                     c->scratch_map, c->ctl};
@@ -234,8 +251,79 @@ extern "C" int srm_nccl_init(srm_ctx *c, const char *id128, int rank, int world)
     return SRM_OK;
 }
 
+static SrmPeers peers_of(srm_ctx *c, int it) {
+    SrmPeers p;
+    if (c->p2p) {
+        p.acc = c->d_peer_acc; p.flags = c->d_peer_flags; p.flags_local = c->flags;
+        p.world = c->world; p.rank = c->rank; p.stride = c->acc_stride; p.parity = it & 1;
+    }
+    return p;
+}
+static double *cur_acc(srm_ctx *c, int it) { return c->acc + (c->p2p ? (size_t)(it & 1) * c->acc_stride : 0); }
+
+// Peer-memory all-reduce set-up.  Every rank fills a blob describing its accumulator pair and flag array (CUDA IPC
+// handles + raw pointers + pid), the caller gathers the blobs of all ranks (plumbing), every rank connects.
+// Call after the sites are set (that allocates the accumulators) and before iterating; collective.
+struct SrmP2PBlob {
+    cudaIpcMemHandle_t acc, flags;
+    unsigned long long acc_ptr, flags_ptr;
+    long long pid;
+    int device, pad;
+};
+static_assert(sizeof(SrmP2PBlob) == 160, "blob layout is part of the C ABI");
+
+extern "C" int srm_p2p_info(srm_ctx *c, void *blob160) {
+    if (!c || !blob160) return fail(SRM_ERR_ARG, "srm_p2p_info: null argument");
+    if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_p2p_info: set the sites first");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemset(c->flags, 0, 64 * sizeof(int)));
+    SrmP2PBlob b;
+    memset(&b, 0, sizeof(b));
+    CK(cudaIpcGetMemHandle(&b.acc, c->acc));
+    CK(cudaIpcGetMemHandle(&b.flags, c->flags));
+    b.acc_ptr = (unsigned long long)c->acc; b.flags_ptr = (unsigned long long)c->flags;
+    b.pid = (long long)getpid(); b.device = c->device;
+    memcpy(blob160, &b, sizeof(b));
+    return SRM_OK;
+}
+
+extern "C" int srm_p2p_connect(srm_ctx *c, const void *blobs, int rank, int world) {
+    if (!c || !blobs || world < 1 || world > 64 || rank < 0 || rank >= world)
+        return fail(SRM_ERR_ARG, "srm_p2p_connect: bad argument");
+    CK(cudaSetDevice(c->device));
+    const SrmP2PBlob *b = (const SrmP2PBlob *)blobs;
+    std::vector<const double *> pa((size_t)world);
+    std::vector<int *> pf((size_t)world);
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) { pa[q] = c->acc; pf[q] = c->flags; continue; }
+        if (b[q].pid == (long long)getpid()) {  // same process (tests): raw pointers, peer access if another device
+            if (b[q].device != c->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(b[q].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(SRM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d): %s", b[q].device, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+            pa[q] = (const double *)b[q].acc_ptr; pf[q] = (int *)b[q].flags_ptr;
+        } else {
+            void *p1 = nullptr, *p2 = nullptr;
+            CK(cudaIpcOpenMemHandle(&p1, b[q].acc, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p1);
+            CK(cudaIpcOpenMemHandle(&p2, b[q].flags, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(p2);
+            pa[q] = (const double *)p1; pf[q] = (int *)p2;
+        }
+    }
+    if (!c->d_peer_acc) CK(cudaMalloc((void **)&c->d_peer_acc, 64 * sizeof(void *)));
+    if (!c->d_peer_flags) CK(cudaMalloc((void **)&c->d_peer_flags, 64 * sizeof(void *)));
+    CK(cudaMemcpy((void *)c->d_peer_acc, pa.data(), world * sizeof(void *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy((void *)c->d_peer_flags, pf.data(), world * sizeof(void *), cudaMemcpyHostToDevice));
+    c->world = world; c->rank = rank; c->p2p = world > 1;
+    return SRM_OK;
+}
+
 static int allreduce_acc(srm_ctx *c) {
-    if (!c->comm) return SRM_OK;
+    if (!c->comm || c->p2p) return SRM_OK;  // peer-memory mode: the update kernel pulls the partial sums itself
     int e = g_nccl.AllReduce(c->acc, c->acc, 4 * (size_t)c->Kcap + 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
     if (e) return fail(SRM_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
     return SRM_OK;
@@ -394,6 +482,39 @@ extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
     return fail(SRM_ERR_ARG, "srm_set_option: unknown option %s", name);
 }
 
+// Site extraction in the order delaunayInput scans the label map (delaunay.h:46-57: x outer, y inner; sites are
+// pixels with label == self that are not constraint pixels; point = (x*scale + l, y*scale + b)).  The reference
+// downloads the 2N-short label map and scans it on the host; here the K-entry site list is read back instead.
+extern "C" int srm_extract_sites(srm_ctx *c, const unsigned char *mask_host, double scale, double l, double b,
+                                 double *points_xy, int capacity, int *num_out) {
+    if (!c || !num_out) return fail(SRM_ERR_ARG, "srm_extract_sites: null argument");
+    if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_extract_sites: no sites set");
+    SrmCtl h;
+    int rc = fetch_ctl(c, &h);
+    if (rc) return rc;
+    std::vector<int> all((size_t)(h.K > 0 ? h.K : 0));
+    if (h.K > 0) CK(cudaMemcpy(all.data(), c->sites[current_buffer(c)], all.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    std::vector<unsigned> keys;  // x in the high half: sorting by key = x outer, y inner
+    keys.reserve(all.size());
+    const int n = c->g.n;
+    for (int v : all) {
+        if (v == SRM_SENT) continue;
+        const int x = srm_x(v), y = srm_y(v);
+        if (mask_host && mask_host[(size_t)y * n + x]) continue;
+        keys.push_back(((unsigned)x << 16) | (unsigned)y);
+    }
+    std::sort(keys.begin(), keys.end());
+    *num_out = (int)keys.size();
+    if (points_xy) {
+        const int k = std::min(capacity, (int)keys.size());
+        for (int i = 0; i < k; ++i) {
+            points_xy[2 * i] = (double)(keys[i] >> 16) * scale + l;
+            points_xy[2 * i + 1] = (double)(keys[i] & 0xffffu) * scale + b;
+        }
+    }
+    return SRM_OK;
+}
+
 extern "C" int srm_set_omega(srm_ctx *c, float omega) {
     if (!c) return fail(SRM_ERR_ARG, "null ctx");
     CK(cudaSetDevice(c->device));
@@ -406,18 +527,21 @@ extern "C" int srm_set_omega(srm_ctx *c, float omega) {
 // Inside the loop both agree until a stop; after a stop every kernel is a no-op, so using the
 // host parity for the (skipped) launches is harmless.  For calls outside the loop (final labelling)
 // the parity is read back from the device.
-static int label_with(srm_ctx *c, int buf, int respect_stop, int accumulate, int want_energy) {
+static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy) {
+    const int buf = it & 1;
+    double *acc = cur_acc(c, it);
     srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop);
     srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop);
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
         CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                           c->idmap, c->acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, c->dbg_stats));
+                           c->idmap, acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, c->dbg_stats));
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
     CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
-                      c->acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
+                      acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
+    if (accumulate) srm_launch_signal(c->stream, c->ctl, peers_of(c, it), respect_stop);
     return SRM_OK;
 }
 
@@ -432,7 +556,7 @@ extern "C" int srm_label(srm_ctx *c) {
     int rc = require_ready(c, "srm_label", false);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
-    rc = label_with(c, current_buffer(c), 0, 0, 0);
+    rc = label_with(c, c->it_host, 0, 0, 0);
     if (rc) return rc;
     c->labelled = true;
     return SRM_OK;
@@ -444,7 +568,7 @@ extern "C" int srm_label_accumulate(srm_ctx *c, int want_energy) {
     int rc = require_ready(c, "srm_label_accumulate", true);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
-    rc = label_with(c, current_buffer(c), 0, 1, want_energy);
+    rc = label_with(c, c->it_host, 0, 1, want_energy);
     if (rc) return rc;
     c->labelled = true;
     return SRM_OK;
@@ -455,8 +579,9 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     if (rc) return rc;
     if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
     CK(cudaSetDevice(c->device));
-    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, c->acc, c->Kcap, nullptr, nullptr, c->ctl,
-                   want_energy, 0);
+    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, cur_acc(c, c->it_host), c->Kcap, nullptr,
+                   nullptr, c->ctl, want_energy, 0);
+    srm_launch_signal(c->stream, c->ctl, peers_of(c, c->it_host), 0);
     CK(cudaGetLastError());
     return SRM_OK;
 }
@@ -464,8 +589,8 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
 extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles) {
     if (!c || !device_ptr || !num_doubles) return fail(SRM_ERR_ARG, "srm_acc_buffer: null argument");
     if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_acc_buffer: sites not set");
-    *device_ptr = c->acc;
-    *num_doubles = 4 * (size_t)c->Kcap + 4;
+    *device_ptr = cur_acc(c, c->it_host);
+    *num_doubles = c->acc_stride;
     return SRM_OK;
 }
 
@@ -478,7 +603,7 @@ extern "C" int srm_update(srm_ctx *c) {
     CK(cudaSetDevice(c->device));
     const int buf = current_buffer(c);
     srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
-                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, (c->it_host % 10) == 0, 0, 0);
+                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, (c->it_host % 10) == 0, 0, 0, peers_of(c, c->it_host));
     CK(cudaGetLastError());
     c->labelled = false;
     c->it_host += 1;
@@ -493,13 +618,13 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     int it = c->it_host;
     for (int i = 0; i < iters; ++i, ++it) {
         const int buf = it & 1, want_energy = (it % 10) == 0;
-        rc = label_with(c, buf, 1, 1, want_energy);
+        rc = label_with(c, it, 1, 1, want_energy);
         if (rc) return rc;
-        rc = allreduce_acc(c);  // no-op for a single band
+        rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
         if (rc) return rc;
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
                           c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
-                          stop_rule, 1);
+                          stop_rule, 1, peers_of(c, it));
     }
     CK(cudaGetLastError());
     c->it_host = it;
@@ -529,26 +654,28 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         const int buf = it & 1, want_energy = (it % 10) == 0;
         cudaEvent_t *e = &ev[(size_t)i * 6];
         CK(cudaEventRecord(e[0], c->stream));
+        double *acc = cur_acc(c, it);
         srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1);
         srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1);
         CK(cudaEventRecord(e[1], c->stream));
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {
             CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                               c->idmap, c->acc, c->Kcap, c->ctl, 1, want_energy, 1, c->dbg_stats));
+                               c->idmap, acc, c->Kcap, c->ctl, 1, want_energy, 1, c->dbg_stats));
             rows = c->ovf_rows;
             count = &c->ctl->ovf;
         }
         CK(cudaEventRecord(e[2], c->stream));
         CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
-                          c->acc, c->Kcap, c->ctl, 1, want_energy, 1));
+                          acc, c->Kcap, c->ctl, 1, want_energy, 1));
         CK(cudaEventRecord(e[3], c->stream));
+        srm_launch_signal(c->stream, c->ctl, peers_of(c, it), 1);
         rc = allreduce_acc(c);
         if (rc) return rc;
         CK(cudaEventRecord(e[4], c->stream));
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
                           c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
-                          stop_rule, 1);
+                          stop_rule, 1, peers_of(c, it));
         CK(cudaEventRecord(e[5], c->stream));
     }
     CK(cudaGetLastError());

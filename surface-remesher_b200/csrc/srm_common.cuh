@@ -21,6 +21,7 @@ struct SrmCtl {
     float lastE;    // lastEnergy
     float E;        // Energy (float like the reference)
     int ovf;        // rows handed to the robust path by the band kernel (this labelling)
+    int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
     unsigned long long prof[16];  // optional per-phase clock / element counters of the band kernel (dbg & 1)
 };
@@ -55,6 +56,16 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Peer view of the row-band accumulators (fused all-reduce over NVLink peer memory, srm_lloyd.cu).
+struct SrmPeers {
+    const double *const *acc = nullptr;  // device array [world]: base of every rank's accumulator pair
+    int *const *flags = nullptr;         // device array [world]: every rank's arrival-flag array
+    int *flags_local = nullptr;          // this rank's flag array (slot q = last iteration rank q finished accumulating)
+    int world = 1, rank = 0;
+    size_t stride = 0;                   // doubles per accumulator buffer (two buffers, used by iteration parity)
+    int parity = 0;
+};
+
 // ---- launchers (host), one per pipeline stage; all asynchronous on `st`.
 struct SrmGrid {           // geometry of one context
     int n, row0, row1;
@@ -85,7 +96,8 @@ void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const 
                     const SrmCtl *ctl, int want_energy, int respect_stop);
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
                        const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
-                       int stop_rule, int respect_stop);
+                       int stop_rule, int respect_stop, SrmPeers peers = SrmPeers());
+void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop);
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
                                int *blockoff, int *total_out, int count_only);
 void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out);

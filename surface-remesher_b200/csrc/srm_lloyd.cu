@@ -141,10 +141,40 @@ void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, i
 // with atomicMin(id); the smallest id survives and the others become holes (SRM_SENT) in the list —
 // the reference merges sites the same way, by overwriting one pixel (gcvt.cu:779-780).  The list is
 // never compacted, so ids (accumulator slots) are stable and identical on every rank.
-__global__ void k_update_pos(const int *__restrict__ sites, const double *__restrict__ acc,
-                             const float *__restrict__ density, const unsigned char *__restrict__ mask, int n,
-                             const SrmCtl *__restrict__ ctl, int *__restrict__ newpos, int *claim, int respect_stop) {
+__device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const volatile int *)p; }
+
+// Fused all-reduce (row bands on several GPUs): every rank signals "my accumulators of iteration it are complete"
+// into every peer's flag array (k_signal, after the band kernel); k_update_pos waits for all arrivals and then pulls
+// each site's partial sums straight from the peers' accumulators over NVLink (cache-bypassing loads, fixed rank
+// order, so every rank computes bit-identical totals and the replicated update stays consistent).  Accumulators are
+// double-buffered by iteration parity; a buffer is cleared one iteration after its use, when every peer has
+// provably finished reading it (they have signalled the next iteration).
+__global__ void k_signal(SrmCtl *ctl, SrmPeers p, int respect_stop) {
     if (respect_stop && ctl->stop) return;
+    const int target = ctl->it + 1;
+    __threadfence_system();
+    if ((int)threadIdx.x < p.world) *(volatile int *)(p.flags[threadIdx.x] + p.rank) = target;
+}
+
+void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop) {
+    if (peers.world > 1) k_signal<<<1, 32, 0, st>>>(ctl, peers, respect_stop);
+}
+
+__global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const float *__restrict__ density,
+                             const unsigned char *__restrict__ mask, int n, SrmCtl *ctl, int *__restrict__ newpos,
+                             int *claim, int respect_stop, SrmPeers peers) {
+    if (respect_stop && ctl->stop) return;
+    if (peers.world > 1) {  // wait for every rank's accumulators of this iteration
+        if (threadIdx.x == 0) {
+            const int target = ctl->it + 1;
+            for (int q = 0; q < peers.world; ++q) {
+                long long spins = 0;
+                while (ld_volatile_int(peers.flags_local + q) < target)
+                    if (++spins > (1ll << 28)) { ctl->p2p_timeout = 1; break; }  // fail-safe: never hang the GPU
+            }
+        }
+        __syncthreads();
+    }
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     const int p = sites[id];
@@ -152,8 +182,18 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *__rest
     const int tx = srm_x(p), ty = srm_y(p);
     int rx = tx, ry = ty;
     if (!(mask && mask[(size_t)ty * n + tx])) {
-        const double *a = acc + 4 * (size_t)id;
-        const float pW = (float)a[0], pX = (float)a[1], pY = (float)a[2];
+        double sW = 0, sX = 0, sY = 0;
+        if (peers.world > 1) {
+            for (int q = 0; q < peers.world; ++q) {
+                const double *a = peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)id;
+                const double2 wx = __ldcv(reinterpret_cast<const double2 *>(a));
+                sW += wx.x; sX += wx.y; sY += __ldcv(a + 2);
+            }
+        } else {
+            const double *a = acc + 4 * (size_t)id;
+            sW = a[0]; sX = a[1]; sY = a[2];
+        }
+        const float pW = (float)sW, pX = (float)sX, pY = (float)sY;
         const float omega = ctl->omega;
         const float _x = __fdiv_rn(pX, pW), _y = __fdiv_rn(pY, pW);
         const float fx = __fadd_rn(__fmaf_rn(__fsub_rn(_x, (float)tx), omega, (float)tx), 0.5f);
@@ -173,8 +213,8 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *__rest
 // and apply the stopping rule.
 __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict__ newpos, const int *__restrict__ claim,
                                                            int n, SrmCtl *ctl, int *__restrict__ sites_out,
-                                                           double *__restrict__ acc, int Kcap, int want_energy,
-                                                           int stop_rule, int respect_stop) {
+                                                           double *acc, int Kcap, int want_energy, int stop_rule,
+                                                           int respect_stop, SrmPeers peers) {
     __shared__ int is_last;
     if (respect_stop && ctl->stop) return;  // set only by a previous launch's last block
     const int id = blockIdx.x * UPD_NT + threadIdx.x;
@@ -183,7 +223,9 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
         const int p = newpos[id];
         if (p != SRM_SENT) alive = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
         sites_out[id] = alive ? p : SRM_SENT;
-        double *a = acc + 4 * (size_t)id;  // clear for the next iteration
+        // clear for a later iteration: the buffer just used (single GPU), or the other one of the pair (peers may
+        // still be reading the current one; the other one was last read an iteration ago)
+        double *a = acc + (peers.world > 1 ? (size_t)(peers.parity ^ 1) * peers.stride : 0) + 4 * (size_t)id;
         a[0] = 0; a[1] = 0; a[2] = 0; a[3] = 0;
     }
     const int c = __syncthreads_count(alive);
@@ -197,10 +239,19 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
     __threadfence();
     ctl->nlive = atomicExch(&ctl->live_acc, 0);
     ctl->ticket = 0;
-    double *acc_energy = acc + 4 * (size_t)Kcap;
-    if (want_energy) {
-        ctl->E = (float)(acc_energy[0] / ((double)n * (double)n));
-        acc_energy[0] = 0;
+    if (peers.world > 1) {
+        if (want_energy) {
+            double e = 0;
+            for (int q = 0; q < peers.world; ++q) e += __ldcv(peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)Kcap);
+            ctl->E = (float)(e / ((double)n * (double)n));
+        }
+        acc[(size_t)(peers.parity ^ 1) * peers.stride + 4 * (size_t)Kcap] = 0;
+    } else {
+        double *acc_energy = acc + 4 * (size_t)Kcap;
+        if (want_energy) {
+            ctl->E = (float)(acc_energy[0] / ((double)n * (double)n));
+            acc_energy[0] = 0;
+        }
     }
     const int it = ctl->it + 1;
     ctl->it = it;
@@ -216,11 +267,12 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
 
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
                        const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
-                       int stop_rule, int respect_stop) {
+                       int stop_rule, int respect_stop, SrmPeers peers) {
+    // acc: single GPU: the accumulator buffer; peers: the BASE of this rank's buffer pair
     const int k1 = Kcap > 0 ? Kcap : 1;
-    k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop);
+    k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop, peers);
     k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
-                                                                     stop_rule, respect_stop);
+                                                                     stop_rule, respect_stop, peers);
 }
 
 // ------------------------------------------------------------------ dense seed map -> site list

@@ -101,13 +101,24 @@ class ShardedLloyd:
         self.engine.update()
         self.it += 1
 
-    def bind_native_collective(self):
-        """world > 1 with the CUDA engine: hand the all-reduce to libsrm itself (NCCL communicator created from an id
-        broadcast through torch.distributed), so that run() is one C++ loop without per-iteration Python."""
+    def bind_native_collective(self, mode="p2p"):
+        """world > 1 with the CUDA engine: hand the all-reduce to libsrm itself, so that run() is one C++ loop without
+        per-iteration Python.  mode "p2p": fused all-reduce over peer memory (the update kernel pulls the partial sums
+        from the peers over NVLink; CUDA IPC handles gathered through torch.distributed).  mode "nccl": an NCCL
+        all-reduce issued by libsrm on its stream (communicator id broadcast through torch.distributed).
+        Call after set_inputs()."""
         if self.world == 1 or not hasattr(self.engine, "ctx"):
             return False
         import torch
         dev = self.engine.device
+        if mode == "p2p":
+            mine = torch.tensor(list(self.engine.ctx.p2p_info()), dtype=torch.uint8, device=dev)
+            allb = [torch.zeros(160, dtype=torch.uint8, device=dev) for _ in range(self.world)]
+            self.dist.all_gather(allb, mine)
+            self.engine.ctx.p2p_connect([bytes(t.cpu().tolist()) for t in allb], self.rank, self.world)
+            self.dist.barrier()
+            self.native = True
+            return True
         if self.rank == 0:
             raw = self.engine.ctx.nccl_unique_id()
             t = torch.tensor(list(raw), dtype=torch.uint8, device=dev)

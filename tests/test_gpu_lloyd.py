@@ -217,3 +217,52 @@ def test_full_size_properties(n, k, kind):
     seedmap[sites[:, 1], sites[:, 0], 0] = sites[:, 0]; seedmap[sites[:, 1], sites[:, 0], 1] = sites[:, 1]
     exp = O.label_exact(seedmap)
     assert (lab != exp).sum() == 0
+
+
+def test_extract_sites_matches_delaunay_input_scan():
+    """f1: the CDT input points, in the order delaunay.h:46-57 produces them from the label map."""
+    import surface_remesher_b200 as S
+    n = 512
+    dens, mask, seeds = _case("c3", n, 2000)
+    scale, l, b = 0.37, -1.5, 2.25
+    with S.Context(n) as c:
+        c.set_density(dens); c.set_mask(mask); c.set_site_map(seeds)
+        c.iterate(7)
+        c.label()
+        lab = c.get_labels()
+        pts = c.extract_sites(mask, scale, l, b)
+    exp = []
+    for i in range(n):          # x outer
+        for j in range(n):      # y inner
+            if not mask[j, i] and lab[j, i, 0] == i and lab[j, i, 1] == j:
+                exp.append((i * scale + l, j * scale + b))
+    assert np.array_equal(pts, np.array(exp))
+
+
+def test_two_band_contexts_fused_peer_allreduce():
+    """The fused all-reduce (update kernel pulls the partial sums from peer accumulators, arrival flags, parity
+    double buffering) with two band contexts of one process on one GPU: no collective call, no Python per step."""
+    import surface_remesher_b200 as S
+    n = 512
+    dens, mask, seeds = _case("c3", n, 3000)
+    ctxs = []
+    for (r0, r1) in S.row_bands(n, 2):
+        c = S.Context(n, r0, r1)
+        c.set_density(dens); c.set_mask(mask); c.set_site_map(seeds)
+        ctxs.append(c)
+    blobs = [c.p2p_info() for c in ctxs]
+    for r, c in enumerate(ctxs):
+        c.p2p_connect(blobs, r, 2)
+    iters = 23
+    for c in ctxs:
+        c.iterate(iters, stop_rule=False)      # both loops are enqueued asynchronously and meet on the GPU
+    labs = []
+    for c in ctxs:
+        c.label(); labs.append(c.get_labels())
+    exp, it, en, om = O.gcvt(seeds, dens, mask, iters, stop_rule=0)
+    full = np.concatenate(labs, 0)
+    assert (full != exp).sum() == 0
+    for c in ctxs:
+        st = c.state()
+        assert st["iterations"] == iters and st["omega"] == np.float32(om)
+        c.close()
