@@ -257,22 +257,22 @@ def run_ours(args):
                    "stop_rule": "off (fixed step count); energy every 10th step like the reference"},
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "iterations_per_call": e2e_iters, "api": "gCVT(host buffers)" if world == 1 else "ShardedLloyd(host buffers)"},
-        "gpu_launches": 6 * K * world,  # k_bits, k_carry, k_band, k_row, k_update_pos, k_update_resolve per step and rank
+        "gpu_launches": (6 + (1 if world > 1 and args.collective == "p2p" else 0)) * K * world,  # k_bits, k_carry, k_band, k_row, k_update_pos, k_update_resolve (+ k_signal) per step and rank
         "clocks": clocks,
     }
     if stage is not None and world > 1:
         line["config"]["stages_ms_per_step_rank0"] = {s: v / K for s, v in stage.items()}
     if stage is not None and world == 1:
         row_ms = stage["band_fused"] / K
-        # algorithmic bytes of one k_band launch: per 16-row band and column 8 B (bitmap word + up/dn carries)
-        # = N/2; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
-        alg = 0.5 * N + 52.0 * runs
+        # algorithmic bytes of one k_band launch: per 8-row band and column 8 B (bitmap word + up/dn carries)
+        # = N; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
+        alg = 1.0 * N + 52.0 * runs
         ach = alg / (row_ms / 1e3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; N/2 B + 52 B/run)",
+        line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; N B + 52 B/run)",
                             "runs_per_step": runs, "robust_path_rows": ovf,
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                             "peak_source": peak_src, "ms_per_launch": row_ms,
-                            "note": "integer/latency bound, not HBM bound: see DESIGN.md §roofline",
+                            "note": "latency / instruction-issue bound, not HBM bound: see DESIGN.md section 4",
                             "stages_ms_per_step": {s: v / K for s, v in stage.items()},
                             "step_bytes_per_px_equiv_GBs": {"8B_per_px": 8.0 * N / (ms / K / 1e3) / 1e9}}
     if not args.no_cpu:
@@ -340,8 +340,8 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--sites", type=int, default=100000)

@@ -134,7 +134,9 @@ static int alloc_sites(srm_ctx *c, int K) {
     CK(cudaMalloc(&c->sites[0], k1 * sizeof(int)));
     CK(cudaMalloc(&c->sites[1], k1 * sizeof(int)));
     CK(cudaMalloc(&c->newpos, k1 * sizeof(int)));
-    c->acc_stride = 4 * (size_t)K + 4;  // two buffers: the peer-memory all-reduce alternates them by iteration parity
+    // two buffers (the peer-memory all-reduce alternates them by iteration parity), each: 4K+4 doubles of sums
+    // followed by K "this rank contributed to the site" bytes
+    c->acc_stride = (4 * (size_t)K + 4 + ((size_t)K + 7) / 8 + 3) & ~(size_t)3;  // 32-byte aligned buffers
     CK(cudaMalloc(&c->acc, 2 * c->acc_stride * sizeof(double)));
     CK(cudaMemsetAsync(c->acc, 0, 2 * c->acc_stride * sizeof(double), c->stream));
     c->p2p = false;  // peer mappings refer to the old buffers
@@ -263,7 +265,7 @@ static SrmPeers peers_of(srm_ctx *c, int it) {
     SrmPeers p;
     if (c->p2p) {
         p.acc = c->d_peer_acc; p.flags = c->d_peer_flags; p.flags_local = c->flags;
-        p.world = c->world; p.rank = c->rank; p.stride = c->acc_stride; p.parity = it & 1;
+        p.world = c->world; p.rank = c->rank; p.stride = c->acc_stride; p.parity = it & 1; p.kcap = c->Kcap;
     }
     return p;
 }
@@ -453,8 +455,10 @@ extern "C" int srm_debug_counts(srm_ctx *c, long long *total_runs, int *overflow
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(h.data(), c->rle_cnt, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
     long long tot = 0;
-    for (int v : h) tot += v;
+    int mx = 0;
+    for (int v : h) { tot += v; if (v > mx) mx = v; }
     *total_runs = tot;
+    if (c->dbg_stats) fprintf(stderr, "[srm dbg] runs per row: mean %.1f max %d\n", (double)tot / (double)h.size(), mx);
     SrmCtl hc;
     CK(cudaMemcpy(&hc, c->ctl, sizeof(hc), cudaMemcpyDeviceToHost));
     *overflow_rows = c->robust_only ? c->g.nrows() : hc.ovf;
@@ -538,7 +542,7 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
     const int buf = it & 1;
     double *acc = cur_acc(c, it);
     srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop);
-    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop);
+    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1);
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
         CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
@@ -597,7 +601,7 @@ extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles
     if (!c || !device_ptr || !num_doubles) return fail(SRM_ERR_ARG, "srm_acc_buffer: null argument");
     if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_acc_buffer: sites not set");
     *device_ptr = cur_acc(c, c->it_host);
-    *num_doubles = c->acc_stride;
+    *num_doubles = 4 * (size_t)c->Kcap + 4;
     return SRM_OK;
 }
 
@@ -663,7 +667,7 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         CK(cudaEventRecord(e[0], c->stream));
         double *acc = cur_acc(c, it);
         srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1);
-        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1);
+        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1, c->g.row0, c->g.row1);
         CK(cudaEventRecord(e[1], c->stream));
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {

@@ -377,6 +377,7 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
                             atomicAdd(a, W);
                             atomicAdd(a + 1, X);
                             atomicAdd(a + 2, (double)Y * W);
+                            reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id[q]] = 1;
                         } else if (W == -1.5) a[3] = X;
                         if (want_energy) e_loc += (xb[q] - xa) - 2.0 * (double)xx[q] * X + (double)(HH[q]) * W;
                     }

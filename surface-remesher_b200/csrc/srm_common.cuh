@@ -64,6 +64,7 @@ struct SrmPeers {
     int *flags_local = nullptr;          // this rank's flag array (slot q = last iteration rank q finished accumulating)
     int world = 1, rank = 0;
     size_t stride = 0;                   // doubles per accumulator buffer (two buffers, used by iteration parity)
+    int kcap = 0;                        // sites per buffer: 4*kcap+4 doubles of sums, then kcap "touched" bytes
     int parity = 0;
 };
 
@@ -76,7 +77,7 @@ struct SrmGrid {           // geometry of one context
 void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
                      int *claim, int respect_stop);
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop);
+                      int respect_stop, int row0, int row1);
 // fused fast path (srm_band.cu)
 cudaError_t srm_band_setup(int n);
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,

@@ -95,7 +95,8 @@ __device__ __forceinline__ void env_merge(const EnvSmem &s, int g0, int gm, int 
 // kernelScan_Y, gcvt.cu:591-732, and of kernelCalcEnergy, :788-802).  Returns the lane's energy part.
 __device__ __forceinline__ double acc_row(const int2 *rr, int cnt, const double2 *__restrict__ p2,
                                           const double *__restrict__ pxx, const int *__restrict__ idmap, int n, int Y,
-                                          double *__restrict__ acc, int want_energy, int lane, int abl = 0) {
+                                          double *__restrict__ acc, int Kcap, int want_energy, int lane, int abl = 0) {
+    unsigned char *touched = reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4);  // per-site "this rank contributed"
     double e_loc = 0;
     double2 carry = make_double2(0, 0);  // prefix at the end of the previous run
     double carryxx = 0;
@@ -125,6 +126,7 @@ __device__ __forceinline__ double acc_row(const int2 *rr, int cnt, const double2
                 atomicAdd(a, W);
                 atomicAdd(a + 1, X);
                 atomicAdd(a + 2, (double)Y * W);
+                touched[id] = 1;
             } else if (W == -1.0) a[3] = X;  // keep the loads alive
             if (want_energy) {
                 const int dy = sy - Y;

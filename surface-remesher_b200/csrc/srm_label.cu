@@ -114,7 +114,10 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
 }
 
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop) {
+                      int respect_stop, int row0, int row1) {
+    // (A band-restricted scan — one thread per column walking outward from the band — was measured at 69 us against
+    // 12 us for this segmented full-column scan: too little parallelism, dependent loads.  All ranks scan everything.)
+    (void)row0; (void)row1;
     dim3 grid(n / 32), block(32, CARRY_SEG);
     const int wps = (n >> 5) / CARRY_SEG;  // n multiple of 256 -> integral
     switch (wps) {
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
         __syncthreads();
         if (accumulate && w == 0) {
             double e_loc = acc_row(rle + (size_t)r * n, wtot[0], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, Y, acc,
-                                   want_energy, lane);
+                                   Kcap, want_energy, lane);
             if (want_energy) {
                 e_loc = warp_sum(e_loc);
                 if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);

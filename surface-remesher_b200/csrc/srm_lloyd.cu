@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
     for (int q = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5); q < total; q += nwarps) {
         const int r = rows ? rows[q] : q;
         e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, row0 + r, acc,
-                         want_energy, lane);
+                         Kcap, want_energy, lane);
     }
     if (want_energy) {
         e_loc = warp_sum(e_loc);
@@ -185,9 +185,15 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
         double sW = 0, sX = 0, sY = 0;
         if (peers.world > 1) {
             for (int q = 0; q < peers.world; ++q) {
-                const double *a = peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)id;
-                const double2 wx = __ldcv(reinterpret_cast<const double2 *>(a));
-                sW += wx.x; sX += wx.y; sY += __ldcv(a + 2);
+                // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
+                // cell spans one or two bands, so only those ranks' sums are pulled over NVLink
+                const double *base = peers.acc[q] + (size_t)peers.parity * peers.stride;
+                const unsigned char *tq = reinterpret_cast<const unsigned char *>(base + 4 * (size_t)peers.kcap + 4);
+                if (__ldcv(tq + id)) {
+                    const double *a = base + 4 * (size_t)id;
+                    const double2 wx = __ldcv(reinterpret_cast<const double2 *>(a));
+                    sW += wx.x; sX += wx.y; sY += __ldcv(a + 2);
+                }
             }
         } else {
             const double *a = acc + 4 * (size_t)id;
@@ -225,7 +231,9 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
         sites_out[id] = alive ? p : SRM_SENT;
         // clear for a later iteration: the buffer just used (single GPU), or the other one of the pair (peers may
         // still be reading the current one; the other one was last read an iteration ago)
-        double *a = acc + (peers.world > 1 ? (size_t)(peers.parity ^ 1) * peers.stride : 0) + 4 * (size_t)id;
+        double *abase = acc + (peers.world > 1 ? (size_t)(peers.parity ^ 1) * peers.stride : 0);
+        double *a = abase + 4 * (size_t)id;
+        reinterpret_cast<unsigned char *>(abase + 4 * (size_t)Kcap + 4)[id] = 0;
         a[0] = 0; a[1] = 0; a[2] = 0; a[3] = 0;
     }
     const int c = __syncthreads_count(alive);
