@@ -213,22 +213,42 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
     const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
 
     PROF_T0();
-    // ---- Phase A, pass 1: live mask of every 8-column block (30 owned blocks per step + one halo block each side)
+    // ---- Phase A, pass 1: live mask of every 8-column block (30 owned blocks per step + one halo block each side).
+    // Live columns are staged, in order, in the warp's own (still unused) element buffer so that the list can be
+    // assembled by a plain copy once the per-warp offsets are known.
+    __shared__ int stage_ovf;
+    if (t == 0) stage_ovf = 0;
+    uint2 *stage = reinterpret_cast<uint2 *>(buf0 + (size_t)w * C);
+    constexpr int STAGE_CAP = C / 2;
     int mycount = 0;
+    bool staged = true;
     for (int b0 = bw0; b0 < bw1; b0 += 30) {
         const int b = b0 - 1 + lane;
         Col8 col;
         col.M = SRM_BIG;
         if (b >= 0 && b < nb) load_col8<R>(bits, up, dn, wrow + (size_t)b * 8, j, k0, Y0, col);
         const int ML = __shfl_up_sync(0xffffffffu, col.M, 1), MR = __shfl_down_sync(0xffffffffu, col.M, 1);
+        unsigned live = 0;
         if (lane >= 1 && lane <= 30 && b < bw1) {
-            const unsigned live = live_mask<R>(col, ML, MR);
+            live = live_mask<R>(col, ML, MR);
             masks[b] = (unsigned char)live;
-            mycount += __popc(live);
         }
+        const int cnt = __popc(live);
+        const int incl = warp_incl_scan(cnt, lane);
+        const int tot = __shfl_sync(0xffffffffu, incl, 31);
+        if (staged && mycount + tot <= STAGE_CAP) {
+            int o = mycount + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (live & (1u << k)) {
+                    stage[o] = make_uint2((unsigned)(b * 8 + k) | (col.inb[k] << 16),
+                                          ((unsigned)col.U[k] & 0xffffu) | ((unsigned)col.D[k] << 16));
+                    ++o;
+                }
+        } else staged = false;
+        mycount += tot;
     }
-    for (int o = 16; o > 0; o >>= 1) mycount += __shfl_xor_sync(0xffffffffu, mycount, o);
-    if (lane == 0) wcnt[w] = mycount;
+    if (lane == 0) { wcnt[w] = mycount; if (!staged) stage_ovf = 1; }
     __syncthreads();
     int mb = 0, wbase = 0;
 #pragma unroll
@@ -238,8 +258,11 @@ __global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ b
         if (t < R) ovf_rows[atomicAdd(&ctl->ovf, 1)] = rb + t;
         return;
     }
-    // ---- Phase A, pass 2: write the band list in column order
-    {
+    if (!stage_ovf) {
+        // ---- assemble the band list: copy the staged entries to their place
+        for (int i = lane; i < mycount; i += 32) L[wbase + i] = stage[i];
+    } else {
+        // ---- fallback (a warp's staging area overflowed): recompute the live columns and write the list in order
         int base = wbase;
         for (int b0 = bw0; b0 < bw1; b0 += 32) {
             const int b = b0 + lane;

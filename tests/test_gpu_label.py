@@ -105,3 +105,32 @@ def test_jfa_matches_cpu_jfa_and_error_rate():
     d_e = (exact[..., 0].astype(np.int64) - xs) ** 2 + (exact[..., 1].astype(np.int64) - ys) ** 2
     assert (d_j < d_e).sum() == 0           # JFA can never beat the exact distance
     assert (d_j > d_e).mean() < 1e-3        # and is wrong on well under 0.1 % of pixels
+
+
+def test_no_sites_and_single_site():
+    """Empty site set: every label is MARKER (like the oracle); one site: every pixel takes it."""
+    import surface_remesher_b200 as S
+    n = 256
+    empty = np.full((n, n, 2), I.MARK, np.int16)
+    with S.Context(n) as c:
+        c.set_site_map(empty)
+        c.label()
+        got = c.get_labels()
+    assert (got == I.MARK).all()
+    one = empty.copy(); one[200, 13] = (13, 200)
+    got = _label(one)
+    assert (got[..., 0] == 13).all() and (got[..., 1] == 200).all()
+
+
+def test_gcvt_with_zero_density_everywhere_keeps_sites():
+    """density == 0: no free site may move (gcvt.cu:777), constrained sites stay; W = 0 gives NaN centroids that must
+    not crash or move anything."""
+    import surface_remesher_b200 as S
+    n = 256
+    dens = np.zeros((n, n), np.float32)
+    mask = np.zeros((n, n), np.uint8)
+    seeds = I.random_sites(n, 50, 3)
+    vor = seeds.copy()
+    S.gCVT(vor, dens, mask, n, 1, 12)
+    assert I.site_set(vor) == I.site_set(seeds)
+    assert (vor != O.label_exact(seeds)).sum() == 0
