@@ -60,6 +60,28 @@ def main():
         print(name, json.dumps(rec), file=sys.stderr, flush=True)
         del dens, mask, vor
 
+    # C5: batch of independent 2048^2 meshes on one GPU ("replicas"): several contexts driven from threads, each on
+    # its own stream, so that the small grids (128 bands = 128..256 CTAs each) fill the GPU together
+    import threading
+    n, k = 2048, 10000
+    dens, mask, vor = seeded(n, k, "c3")
+    for conc in (1, 2, 4, 8):
+        ctxs = []
+        for _ in range(conc):
+            c = S.Context(n); c.set_density(dens); c.set_mask(mask); c.set_site_map(vor); c.iterate(5); ctxs.append(c)
+        for c in ctxs: c.synchronize()
+        iters = 200
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=lambda c=c: (c.iterate(iters), c.synchronize())) for c in ctxs]
+        for t in th: t.start()
+        for t in th: t.join()
+        dt = time.perf_counter() - t0
+        out[f"C5 batch 2048^2 x{conc} concurrent"] = {"mesh_iterations_per_s": conc * iters / dt,
+                                                      "meshes_of_100_iterations_per_s": conc * iters / dt / 100}
+        print(f"C5 x{conc}", out[f"C5 batch 2048^2 x{conc} concurrent"], file=sys.stderr, flush=True)
+        for c in ctxs: c.close()
+    del dens, mask, vor
+
     # JFA family + expand at 8192^2: HBM streaming kernels
     n = 8192
     dens, mask, vor = seeded(n, 100000, "c3")
