@@ -268,9 +268,14 @@ def run_ours(args):
         # = N; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
         alg = 1.0 * N + 52.0 * runs
         ach = alg / (row_ms / 1e3) / 1e9
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of k_band per launch, from the committed ncu capture
+        tp = os.path.join(ROOT, "profiles", "r1_k_band_traffic.json")
+        if n == 8192 and k == 100000 and os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = 0.9 * tj["traffic_normal_step"] + 0.1 * tj["traffic_energy_step"]   # every 10th step computes the energy
         line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; N B + 52 B/run)",
                             "runs_per_step": runs, "robust_path_rows": ovf,
-                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                             "peak_source": peak_src, "ms_per_launch": row_ms,
                             "note": "latency / instruction-issue bound, not HBM bound: see DESIGN.md section 4",
                             "stages_ms_per_step": {s: v / K for s, v in stage.items()},
