@@ -53,8 +53,9 @@ int srm_version(void);
 /* ------------------------------------------------------------ one-shot drop-ins (host buffers) */
 
 /* gCVT (gcvt.cu:1087-1156): voronoi in = seed map, out = label map of the final sites.
- * depth > 1 is clamped like gcvt.cu:1091 and then run as a single level.
- * stats may be NULL. */
+ * depth > 1 (clamped like gcvt.cu:1091 so that the coarsest level is >= 256) runs the reference's coarse-to-fine
+ * loop (gcvt.cu:985-993, 1036-1051, 1110-1147): voronoi in = seed map of side n >> (depth-1) stored in the FIRST
+ * (n >> (depth-1))^2 entries of the n^2 buffer (gcvt.cu:1101-1103), out = n^2 labels.  stats may be NULL. */
 int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
              srm_stats *stats);
 

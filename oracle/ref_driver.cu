@@ -29,6 +29,7 @@ void pbaCVDDensityScaling(int k);
 void pbaCVDComputeWeightedPrefix(int k);
 void pbaCVDComputeCentroid();
 void pbaCVDUpdateSites();
+void pbaCVDZoomIn();
 float pbaCVDCalcEnergy();
 void gCVT(short *Voronoi, float *density_d, bool *mask, int size, int depth, int maxIter);
 void discretization_d(double *points, double *weight, int num_point, int *triangle, int num_tri,
@@ -120,6 +121,35 @@ int ref_loop_timed(const short *seeds, float *density, unsigned char *mask, int 
     cudaEventElapsedTime(ms_out, a, b);
     cudaEventDestroy(a); cudaEventDestroy(b);
     cudaError_t e = cudaDeviceSynchronize();
+    pbaCVDDeinitialization();
+    return e == cudaSuccess ? 0 : -2;
+}
+
+// Multires pieces (a11).  Level `level` (>= 1) of the reference's density pyramid
+// (pbaCVDDensityScaling -> kernelDensityScaling, gcvt.cu:985-993, 497-511): out = (n >> level)^2 floats.
+int ref_pyramid(float *density, unsigned char *mask, int n, int level, float *out) {
+    if (!size_ok(n) || level < 1 || (n >> level) < 256) return -1;
+    gcvtInitialization(n);
+    pba2DInitializeInput(density, (bool *)mask);
+    pbaCVDDensityScaling(level + 1);
+    cudaError_t e = cudaDeviceSynchronize();
+    const size_t s = (size_t)(n >> level);
+    cudaMemcpy(out, pbaDensity[level], s * s * sizeof(float), cudaMemcpyDeviceToHost);
+    pbaCVDDeinitialization();
+    return e == cudaSuccess ? 0 : -2;
+}
+
+// pbaCVDZoomIn (gcvt.cu:1036-1051): seed map of side s -> seed map of side 2s.
+int ref_zoom(const short *seeds_s, int s, short *seeds_2s) {
+    if (!size_ok(2 * s) || s < 256) return -1;
+    gcvtInitialization(2 * s);
+    pbaVoronoi = pbaTextures[0]; pbaTemp = pbaTextures[1]; pbaBuffer = 0;
+    pbaTexSize = s;
+    cudaMemcpy(pbaVoronoi, seeds_s, (size_t)s * s * sizeof(short2), cudaMemcpyHostToDevice);
+    pbaCVDZoomIn();
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(seeds_2s, pbaVoronoi, (size_t)4 * s * s * sizeof(short2), cudaMemcpyDeviceToHost);
+    pbaTexSize = 2 * s;
     pbaCVDDeinitialization();
     return e == cudaSuccess ? 0 : -2;
 }

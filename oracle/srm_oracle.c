@@ -351,6 +351,90 @@ int orc_gcvt(short *vor, const float *density, const uint8_t *mask, int n, int m
     return it;
 }
 
+/* --------------------------------------------------------------- multires (a11) */
+
+/* kernelDensityScaling (gcvt.cu:497-511): 2x2 box filter, float adds in the loop order
+ * x outer / y inner, then /4.0 (a double division of a float, exact).  s = OUTPUT side. */
+void orc_density_scale(const float *in, float *out, int s) {
+    for (int ty = 0; ty < s; ++ty)
+        for (int tx = 0; tx < s; ++tx) {
+            float d = 0;
+            for (int x = 2 * tx; x < 2 * tx + 2; ++x)
+                for (int y = 2 * ty; y < 2 * ty + 2; ++y) d += in[IDX(x, y, 2 * s)];
+            out[IDX(tx, ty, s)] = (float)((double)d / 4.0);
+        }
+}
+
+/* pbaCVDZoomIn = kernelFillShort + kernelZoomIn (gcvt.cu:485-495,1036-1051): a site (x,y) of the
+ * s-sided map becomes the site (2x,2y) of the 2s-sided map.  s = INPUT side. */
+void orc_zoom_in(const short *in, short *out, int s) {
+    size_t N2 = (size_t)4 * s * s;
+    for (size_t i = 0; i < 2 * N2; ++i) out[i] = MARK;
+    for (int y = 0; y < s; ++y)
+        for (int x = 0; x < s; ++x) {
+            size_t i = IDX(x, y, s);
+            if (in[2 * i] == MARK) continue;
+            size_t o = IDX(2 * x, 2 * y, 2 * s);
+            out[2 * o] = (short)(in[2 * i] << 1); out[2 * o + 1] = (short)(in[2 * i + 1] << 1);
+        }
+}
+
+/* gCVT driver with the coarse-to-fine loop (gcvt.cu:1087-1156).  depth is clamped so that the coarsest
+ * level is >= 256 (:1091).  vor: in = seed map of side n >> (depth-1) in the FIRST (n >> (depth-1))^2
+ * entries (:1101-1103), out = n^2 labels of the final sites.  Level L (0 = finest) runs on the L-times
+ * box-filtered density; the constraint mask is indexed with the LEVEL's side on the full-resolution
+ * buffer (kernelUpdateSites is handed constrainMask_d and size = pbaTexSize, :1032-1033), i.e. a coarse
+ * level sees the first s^2 bytes of the mask as an s x s image.  The iteration counter, omega, Energy
+ * and lastEnergy carry over between levels; the energy is scaled by 4^L (:1082); coarse levels stop at
+ * gradient < 3e-1 (:1133), every level runs at least one iteration (do/while).
+ * level_iters (optional, capacity depth) receives the iteration count at the end of each level, coarsest
+ * first (the reference's switch_iter, :1144).  Returns iterations run, or -1 on a bad size. */
+int orc_gcvt_multires(short *vor, const float *density, const uint8_t *mask, int n, int depth, int max_iter,
+                      int stop_rule, int *level_iters, float *omega_out, float *energy_out) {
+    if (depth < 1) depth = 1;
+    for (int i = 0; i < depth; ++i) if ((n >> i) < 256) { depth = i; break; }
+    if (depth < 1) return -1;
+    size_t N = (size_t)n * n;
+    float **dens = (float **)malloc(sizeof(float *) * depth);
+    dens[0] = (float *)density;
+    for (int i = 1; i < depth; ++i) {
+        int s = n >> i;
+        dens[i] = (float *)malloc(sizeof(float) * (size_t)s * s);
+        orc_density_scale(dens[i - 1], dens[i], s);
+    }
+    short *cur = (short *)malloc(sizeof(short) * 2 * N), *nxt = (short *)malloc(sizeof(short) * 2 * N);
+    int s = n >> (depth - 1);
+    memcpy(cur, vor, sizeof(short) * 2 * (size_t)s * s);
+    float Energy = 0, lastEnergy = 1e18f, diffEnergy, gradientEnergy, omega = 2.0f;
+    int it = 0, nl = 0;
+    for (int L = depth - 1; L >= 0; --L) {
+        s = n >> L;
+        do {
+            double E;
+            orc_lloyd_step(cur, dens[L], mask, s, omega, NULL, nxt, (it % 10 == 0) ? &E : NULL);
+            if (it % 10 == 0) Energy = (float)E * powf(2.0f, (float)L * 2.0f);
+            short *t = cur; cur = nxt; nxt = t;
+            ++it;
+            if (it % 10 == 0) {
+                diffEnergy = lastEnergy - Energy;
+                gradientEnergy = (float)(diffEnergy / 10.0);
+                double om = 1.0 + (double)diffEnergy;
+                omega = (float)(om < 2.0 ? om : 2.0);
+                if (stop_rule && (double)gradientEnergy < (L ? 3e-1 : 1e-5)) break;
+                lastEnergy = Energy;
+            }
+        } while (it < max_iter);
+        if (level_iters) level_iters[nl++] = it;
+        if (L) { orc_zoom_in(cur, nxt, s); short *t = cur; cur = nxt; nxt = t; }
+    }
+    orc_label_exact(cur, vor, n);
+    if (omega_out) *omega_out = omega;
+    if (energy_out) *energy_out = Energy;
+    for (int i = 1; i < depth; ++i) free(dens[i]);
+    free(dens); free(cur); free(nxt);
+    return it;
+}
+
 /* --------------------------------------------------------------- rasteriser */
 
 /* discretization.cu:32-85 (Appendix A6).  fp64; nvcc's default -fmad=true contracts

@@ -148,6 +148,7 @@ static int reset_ctl(srm_ctx *c, int K) {
     SrmCtl h;
     memset(&h, 0, sizeof(h));
     h.K = K; h.nlive = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
+    h.escale = 1.0f; h.thresh = 1e-5;                                     // finest level (gcvt.cu:1082,1136)
     h.epoch = ++c->epoch;
     CK(cudaMemcpyAsync(c->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));  // h is a stack object
@@ -355,17 +356,21 @@ extern "C" int srm_synchronize(srm_ctx *c) {
     return SRM_OK;
 }
 
+// pbaCVDComputeWeightedPrefix (gcvt.cu:995-1006), fp64, rows of this band only; c->density is already filled.
+static int density_ready(srm_ctx *c) {
+    srm_launch_prefix(c->stream, c->density + (size_t)c->g.row0 * c->g.n, c->g, c->P2, c->PXX);
+    CK(cudaGetLastError());
+    c->has_density = true;
+    return SRM_OK;
+}
+
 extern "C" int srm_set_density(srm_ctx *c, const float *density, int on_device) {
     if (!c || !density) return fail(SRM_ERR_ARG, "srm_set_density: null argument");
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->density, density, c->N * sizeof(float),
                        on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    // pbaCVDComputeWeightedPrefix (gcvt.cu:995-1006), fp64, rows of this band only
-    srm_launch_prefix(c->stream, c->density + (size_t)c->g.row0 * c->g.n, c->g, c->P2, c->PXX);
-    CK(cudaGetLastError());
     if (!on_device) CK(cudaStreamSynchronize(c->stream));  // pageable source must stay valid
-    c->has_density = true;
-    return SRM_OK;
+    return density_ready(c);
 }
 
 extern "C" int srm_set_mask(srm_ctx *c, const unsigned char *mask, int on_device) {
@@ -795,11 +800,89 @@ extern "C" int srm_release_cache(void) {
     return SRM_OK;
 }
 
+// Loop state handed from one multires level to the next (gcvt.cu:1105-1147 keeps one set of host variables
+// across the levels: the iteration counter, omega, Energy and lastEnergy are NOT reset at a level switch).
+static int carry_ctl(srm_ctx *c, const SrmCtl &prev, int level) {
+    CK(cudaStreamSynchronize(c->stream));
+    SrmCtl h;
+    CK(cudaMemcpy(&h, c->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+    h.it = prev.it; h.omega = prev.omega; h.lastE = prev.lastE; h.E = prev.E; h.stop = 0;
+    h.escale = (float)(1 << (2 * level));         // powf(2, 2 pbaScale), gcvt.cu:1082
+    h.thresh = level ? 3e-1 : 1e-5;               // gcvt.cu:1132-1137
+    CK(cudaMemcpy(c->ctl, &h, sizeof(h), cudaMemcpyHostToDevice));
+    c->it_host = prev.it;
+    c->stopped = false;
+    return SRM_OK;
+}
+
+// Coarse-to-fine gCVT (depth > 1; gcvt.cu:985-993, 1036-1051, 1087-1156).  Level L runs in its own context of side
+// n >> L: density = L-times box-filtered input (on device), constraint mask = the first (n >> L)^2 bytes of the
+// caller's mask read as an image of that side (the reference indexes the full-resolution mask with the level's
+// size, gcvt.cu:1032-1033 / 764-777), sites = the previous level's sites with doubled coordinates.
+// voronoi in: seed map of side n >> (depth-1) in the first entries of the buffer (gcvt.cu:1101-1103).
+static int gcvt_multires(srm_ctx *c0, short *voronoi, const float *density, const unsigned char *mask, int depth,
+                         int max_iter, srm_stats *stats) {
+    const int n = c0->g.n, dev = c0->device;
+    std::vector<srm_ctx *> lev((size_t)depth, nullptr);
+    lev[0] = c0;
+    int rc = SRM_OK;
+    float ms_total = 0;
+    SrmCtl h;
+    memset(&h, 0, sizeof(h));
+    auto cleanup = [&]() { for (int L = 1; L < depth; ++L) if (lev[L]) srm_destroy(lev[L]); };
+#define MR(call) do { rc = (call); if (rc) { cleanup(); return rc; } } while (0)
+#define MRC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return fail(SRM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); } } while (0)
+    MR(srm_set_density(c0, density, 0));
+    for (int L = 1; L < depth; ++L) {
+        MR(srm_create(&lev[L], n >> L, 0, n >> L, dev));
+        MRC(cudaStreamSynchronize(lev[L - 1]->stream));   // the finer density is complete (different streams)
+        srm_launch_density_scale(lev[L]->stream, lev[L - 1]->density, lev[L]->density, n >> L);
+        MRC(cudaGetLastError());
+        MR(density_ready(lev[L]));
+    }
+    for (int L = 0; L < depth; ++L) MR(srm_set_mask(lev[L], mask, 0));  // copies the first (n >> L)^2 bytes
+    MR(srm_set_site_map(lev[depth - 1], voronoi, 0));
+    MRC(cudaMemcpy(&h, lev[depth - 1]->ctl, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int L = depth - 1; L >= 0; --L) {
+        srm_ctx *c = lev[L];
+        MR(carry_ctl(c, h, L));
+        MRC(cudaEventRecord(c->ev0, c->stream));
+        // do { ... } while (gcvtIterations < maxIter): every level runs at least one iteration
+        MR(srm_iterate(c, std::max(1, max_iter - h.it), 1));
+        MRC(cudaEventRecord(c->ev1, c->stream));
+        MR(fetch_ctl(c, &h));
+        float ms = 0;
+        MRC(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        ms_total += ms;
+        if (L) {  // pbaCVDZoomIn: same ids, doubled coordinates, into the buffer the next level reads first
+            srm_ctx *f = lev[L - 1];
+            MR(alloc_sites(f, h.K));
+            MR(reset_ctl(f, h.K));
+            srm_launch_zoom_sites(f->stream, c->sites[current_buffer(c)], f->sites[h.it & 1], h.K);
+            MRC(cudaGetLastError());
+            f->has_sites = true;
+        }
+    }
+    MRC(cudaEventRecord(c0->ev0, c0->stream));
+    MR(srm_label(c0));  // final pba2DCompute (gcvt.cu:1149)
+    MRC(cudaEventRecord(c0->ev1, c0->stream));
+    MRC(cudaEventSynchronize(c0->ev1));
+    float ms = 0;
+    MRC(cudaEventElapsedTime(&ms, c0->ev0, c0->ev1));
+    fill_stats(h, stats, ms_total + ms);
+    MR(srm_get_labels(c0, voronoi, 0));
+    cleanup();
+#undef MR
+#undef MRC
+    return SRM_OK;
+}
+
 extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned char *mask, int n, int depth, int max_iter,
                         srm_stats *stats) {
     if (!voronoi || !density) return fail(SRM_ERR_ARG, "srm_gcvt: null argument");
     if (!valid_n(n)) return fail(SRM_ERR_ARG, "srm_gcvt: n=%d unsupported", n);
-    (void)depth;  // single level; see DESIGN.md (gcvt.h cannot drive depth > 1 either)
+    if (depth < 1) depth = 1;
+    for (int i = 0; i < depth; ++i) if ((n >> i) < 256) { depth = i; break; }  // gcvt.cu:1091
     int dev = 0;
     cudaGetDevice(&dev);
     const bool trace = getenv("SRM_TRACE") != nullptr;
@@ -819,6 +902,12 @@ extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned cha
     }
     srm_ctx *c = g_cache;
     TR("create");
+    if (depth > 1) {
+        rc = gcvt_multires(c, voronoi, density, mask, depth, max_iter, stats);
+        TR("multires");
+        if (rc) { srm_destroy(g_cache); g_cache = nullptr; }
+        return rc;
+    }
     rc = srm_set_density(c, density, 0);
     TR("density");
     if (!rc) rc = srm_set_mask(c, mask, 0);

@@ -451,13 +451,17 @@ static cudaError_t band_setup_one(int smem) {
 }
 
 cudaError_t srm_band_setup(int n) {
-    const int smem = (int)band_smem(n, band_cap(n));
-    cudaError_t e;
-    switch (band_bufcap(n)) {
-        case 1024: e = band_setup_one<1, 1024>(smem); if (e == cudaSuccess) e = band_setup_one<2, 1024>(smem); break;
-        case 1536: e = band_setup_one<1, 1536>(smem); if (e == cudaSuccess) e = band_setup_one<2, 1536>(smem); break;
-        default:   e = band_setup_one<1, 3072>(smem); if (e == cudaSuccess) e = band_setup_one<2, 3072>(smem); break;
-    }
+    // The attribute is per function (and device), not per context: contexts of different sizes coexist (multires
+    // levels, batches), so every instantiation is opted in for the largest grid it serves.
+    (void)n;
+    const int s8 = (int)band_smem(8192, band_cap(8192)), s16 = (int)band_smem(16384, band_cap(16384)),
+              s32 = (int)band_smem(32768, band_cap(32768));
+    cudaError_t e = band_setup_one<1, 1024>(s8);
+    if (e == cudaSuccess) e = band_setup_one<2, 1024>(s8);
+    if (e == cudaSuccess) e = band_setup_one<1, 1536>(s16);
+    if (e == cudaSuccess) e = band_setup_one<2, 1536>(s16);
+    if (e == cudaSuccess) e = band_setup_one<1, 3072>(s32);
+    if (e == cudaSuccess) e = band_setup_one<2, 3072>(s32);
     return e;
 }
 

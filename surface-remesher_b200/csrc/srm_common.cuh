@@ -23,6 +23,8 @@ struct SrmCtl {
     int ovf;        // rows handed to the robust path by the band kernel (this labelling)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
+    float escale;    // multires: energy factor 4^level (gcvt.cu:1082); 1 on the finest level
+    double thresh;   // stopping threshold on the energy gradient: 1e-5 finest, 3e-1 coarse levels (gcvt.cu:1132-1137)
     int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
     unsigned long long prof[16];  // optional per-phase clock / element counters of the band kernel (dbg & 1)
 };
@@ -106,6 +108,9 @@ void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, i
 void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step);
 void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map);
 void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value);
+// multires (gcvt.cu:485-511): 2x2 box filter of the density (s = output side), site zoom x2
+void srm_launch_density_scale(cudaStream_t st, const float *in, float *out, int s);
+void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K);
 
 cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int num_point, const int *tri, int num_tri,
                        float *density, double scale, int n);

@@ -276,8 +276,13 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
 
 static size_t row_smem_bytes(int n) { return (size_t)n * 6; }  // 192 KB at n = 32768
 
+__global__ void k_expand(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt, int n, int *__restrict__ labels);
+
 cudaError_t srm_label_setup(int n) {
-    cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(n));
+    // per function, not per context: opt in for the largest grid (contexts of different sizes coexist)
+    cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(32768));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * (int)sizeof(int));
     if (e != cudaSuccess) return e;
     return srm_band_setup(n);
 }
@@ -339,12 +344,6 @@ __global__ void __launch_bounds__(EXP_NT) k_expand(const int2 *__restrict__ rle,
 
 cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels) {
     size_t sm = (size_t)g.n * sizeof(int);
-    static int configured_for = 0;
-    if (sm > 48 * 1024 && configured_for < g.n) {
-        cudaError_t e = cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        configured_for = g.n;
-    }
     k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, rle_cnt, g.n, labels);
     return cudaGetLastError();
 }

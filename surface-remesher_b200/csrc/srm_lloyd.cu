@@ -251,13 +251,13 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
         if (want_energy) {
             double e = 0;
             for (int q = 0; q < peers.world; ++q) e += __ldcv(peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)Kcap);
-            ctl->E = (float)(e / ((double)n * (double)n));
+            ctl->E = (float)(e / ((double)n * (double)n)) * ctl->escale;
         }
         acc[(size_t)(peers.parity ^ 1) * peers.stride + 4 * (size_t)Kcap] = 0;
     } else {
         double *acc_energy = acc + 4 * (size_t)Kcap;
         if (want_energy) {
-            ctl->E = (float)(acc_energy[0] / ((double)n * (double)n));
+            ctl->E = (float)(acc_energy[0] / ((double)n * (double)n)) * ctl->escale;  // * powf(2, 2 level), gcvt.cu:1082
             acc_energy[0] = 0;
         }
     }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
         const float gradientEnergy = (float)((double)diffEnergy / 10.0);
         const double om = 1.0 + (double)diffEnergy;
         ctl->omega = (float)(om < 2.0 ? om : 2.0);
-        if (stop_rule && (double)gradientEnergy < 1e-5) ctl->stop = 1;
+        if (stop_rule && (double)gradientEnergy < ctl->thresh) ctl->stop = 1;
         else ctl->lastE = ctl->E;
     }
 }
@@ -281,6 +281,38 @@ void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, dou
     k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop, peers);
     k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
                                                                      stop_rule, respect_stop, peers);
+}
+
+// ------------------------------------------------------------------ multires (coarse-to-fine, gcvt.cu:485-511)
+
+// kernelDensityScaling: float adds in the reference's loop order (x outer, y inner), then an exact /4.
+__global__ void __launch_bounds__(256) k_density_scale(const float *__restrict__ in, float *__restrict__ out, int s) {
+    const int tx = blockIdx.x * 32 + (threadIdx.x & 31), ty = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (tx >= s || ty >= s) return;
+    const size_t n2 = 2 * (size_t)s;
+    const float2 a = *reinterpret_cast<const float2 *>(in + (size_t)(2 * ty) * n2 + 2 * tx);
+    const float2 b = *reinterpret_cast<const float2 *>(in + (size_t)(2 * ty + 1) * n2 + 2 * tx);
+    float d = __fadd_rn(0.0f, a.x);   // (2tx, 2ty)
+    d = __fadd_rn(d, b.x);            // (2tx, 2ty+1)
+    d = __fadd_rn(d, a.y);            // (2tx+1, 2ty)
+    d = __fadd_rn(d, b.y);            // (2tx+1, 2ty+1)
+    out[(size_t)ty * s + tx] = d * 0.25f;
+}
+
+void srm_launch_density_scale(cudaStream_t st, const float *in, float *out, int s) {
+    k_density_scale<<<dim3((s + 31) / 32, (s + 7) / 8), 256, 0, st>>>(in, out, s);
+}
+
+// kernelZoomIn on the site list: (x, y) -> (2x, 2y); holes stay holes.
+__global__ void k_zoom_sites(const int *__restrict__ in, int *__restrict__ out, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K) return;
+    const int p = in[i];
+    out[i] = (p == SRM_SENT) ? SRM_SENT : srm_pack(srm_x(p) << 1, srm_y(p) << 1);
+}
+
+void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K) {
+    if (K > 0) k_zoom_sites<<<(K + 255) / 256, 256, 0, st>>>(in, out, K);
 }
 
 // ------------------------------------------------------------------ dense seed map -> site list

@@ -44,6 +44,10 @@ def lib():
         L.orc_lloyd_step.argtypes = [p, p, p, C.c_int, C.c_float, p, p, p]
         L.orc_gcvt.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, p, p]
         L.orc_gcvt.restype = C.c_int
+        L.orc_density_scale.argtypes = [p, p, C.c_int]
+        L.orc_zoom_in.argtypes = [p, p, C.c_int]
+        L.orc_gcvt_multires.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
+        L.orc_gcvt_multires.restype = C.c_int
         L.orc_rasterise.argtypes = [p, p, C.c_int, p, C.c_int, p, C.c_double, C.c_int]
         L.orc_fast_scratch_bytes.argtypes = [C.c_int, C.c_int]
         L.orc_fast_scratch_bytes.restype = C.c_size_t
@@ -138,6 +142,40 @@ def gcvt(seeds, density, mask, max_iter, stop_rule=1):
     om = np.zeros(1, np.float32)
     it = lib().orc_gcvt(_p(vor), _p(d), _p(m), n, int(max_iter), int(stop_rule), _p(en), _p(om))
     return vor, it, en[: (it + 9) // 10].tolist(), float(om[0])
+
+
+def density_scale(density):
+    """kernelDensityScaling: one 2x2 box-filter level."""
+    n = density.shape[0]
+    d = np.ascontiguousarray(density, np.float32)
+    out = np.empty((n // 2, n // 2), np.float32)
+    lib().orc_density_scale(_p(d), _p(out), n // 2)
+    return out
+
+
+def zoom_in(seeds):
+    s = seeds.shape[0]
+    a = np.ascontiguousarray(seeds, np.int16)
+    out = np.empty((2 * s, 2 * s, 2), np.int16)
+    lib().orc_zoom_in(_p(a), _p(out), s)
+    return out
+
+
+def gcvt_multires(coarse_seeds, density, mask, depth, max_iter, stop_rule=1):
+    """Returns (final n^2 label map, iterations, iteration count at the end of each level, omega, Energy)."""
+    n = density.shape[0]
+    s = coarse_seeds.shape[0]
+    vor = np.full((n, n, 2), MARK, np.int16)
+    vor.reshape(-1)[: 2 * s * s] = np.ascontiguousarray(coarse_seeds, np.int16).reshape(-1)
+    d = np.ascontiguousarray(density, np.float32)
+    m = _mask(mask, n)
+    li = np.zeros(16, np.int32); om = np.zeros(1, np.float32); en = np.zeros(1, np.float32)
+    it = lib().orc_gcvt_multires(_p(vor), _p(d), _p(m), n, int(depth), int(max_iter), int(stop_rule), _p(li), _p(om), _p(en))
+    nl = 0
+    dd = max(1, depth)
+    while nl < dd and (n >> nl) >= 256:
+        nl += 1
+    return vor, it, li[:nl].tolist(), float(om[0]), float(en[0])
 
 
 def rasterise(points, weight, triangles, scale, n):

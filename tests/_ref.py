@@ -25,6 +25,8 @@ def lib():
         L.ref_label.argtypes = [p, i]
         L.ref_step.argtypes = [p, p, p, i, f, p, p, p]
         L.ref_loop_timed.argtypes = [p, p, p, i, i, p]
+        L.ref_pyramid.argtypes = [p, p, i, i, p]
+        L.ref_zoom.argtypes = [p, i, p]
         L.ref_discretize.argtypes = [p, p, i, p, i, p, C.c_double, i]
         _lib = L
     return _lib
@@ -68,6 +70,40 @@ def gcvt(seeds, density, mask, max_iter, timed=False):
         return v, it, float(ms[0])
     it = lib().ref_gcvt(_p(v), _p(d), _p(m), n, 1, int(max_iter))
     return v, it
+
+
+def gcvt_multires(coarse_seeds, density, mask, depth, max_iter):
+    """Reference gCVT with depth > 1 (gcvt.cu:1087-1156): the seed map has side n >> (depth-1) and is read from the
+    first entries of the n^2 buffer.  Returns (final n^2 label map, iterations)."""
+    n = density.shape[0]
+    s = coarse_seeds.shape[0]
+    assert s == n >> (depth - 1)
+    v = np.full((n, n, 2), -32768, np.int16)
+    v.reshape(-1)[: 2 * s * s] = np.ascontiguousarray(coarse_seeds, np.int16).reshape(-1)
+    d = np.ascontiguousarray(density, np.float32)
+    m = _mask(mask, n)
+    it = lib().ref_gcvt(_p(v), _p(d), _p(m), n, int(depth), int(max_iter))
+    return v, it
+
+
+def pyramid(density, level):
+    n = density.shape[0]
+    d = np.ascontiguousarray(density, np.float32)
+    m = _mask(None, n)
+    s = n >> level
+    out = np.empty((s, s), np.float32)
+    rc = lib().ref_pyramid(_p(d), _p(m), n, int(level), _p(out))
+    assert rc == 0, rc
+    return out
+
+
+def zoom(seeds):
+    s = seeds.shape[0]
+    a = np.ascontiguousarray(seeds, np.int16)
+    out = np.empty((2 * s, 2 * s, 2), np.int16)
+    rc = lib().ref_zoom(_p(a), s, _p(out))
+    assert rc == 0, rc
+    return out
 
 
 def loop_timed(seeds, density, mask, iters):

@@ -23,8 +23,32 @@ def sites_list(site_map):
     return O.sites_of(site_map)
 
 
+def multires(out):
+    """Coarse-to-fine pieces (a11): pyramid levels, zoomed seed map, whole depth-2/3 runs."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import test_multires as T
+    for name, kind, n, k, depth, iters in [("uni512_d2", "uniform", 512, 400, 2, 60), ("c3_512_d2", "c3", 512, 1000, 2, 80),
+                                           ("c3_1024_d3", "c3", 1024, 1500, 3, 100)]:
+        dens, mask, seeds = T._case(kind, n, k, depth)
+        rec = dict(n=n, k=k, depth=depth, kind=kind, max_iter=iters)
+        for lvl in range(1, depth):
+            p = R.pyramid(dens, lvl)
+            s = n >> lvl
+            rows = (s // 2 - 32, s // 2 + 32)   # keep the fixture small: a 64-row band of every level
+            rec[f"pyr{lvl}"] = p[rows[0]:rows[1]]
+            rec[f"pyr{lvl}_rows"] = np.array(rows)
+        rec["zoom_sites"] = sites_list(R.zoom(seeds))
+        fin, it = R.gcvt_multires(seeds, dens, mask, depth, iters)
+        rec["final_sites"] = sites_list(fin)
+        rec["iterations"] = it
+        np.savez_compressed(os.path.join(out, f"ref_multires_{name}.npz"), **rec)
+        print("multires", name, "ok", it, len(rec["final_sites"]))
+
+
 def main(out):
     os.makedirs(out, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "multires":
+        return multires(out)
     # ---- labelling (pba2DCompute), incl. lattice ties: pins the tie rule A2
     for name, seeds in [
         ("rand256", I.random_sites(256, 700, 101)),
