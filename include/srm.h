@@ -8,6 +8,10 @@
  *                                            float*,double,int)            discretization.h:66, discretization.cu:87
  *   srm_seed        <- putConstrains + randomPoints                        gcvt.h:76-122
  *   srm_generate_mask <- generateMask                                      gcvt.h:143-159
+ *   srm_locate      <- locate(p, mesh, f_loc)                              recover.h:63-83
+ *   srm_recover     <- recover(mesh_2d, mesh_3d, vertex_2d_to_3d, point,
+ *                              triangle, c_points, resMesh)                recover.h:85-153
+ *   srm_extract_sites <- the site scan of delaunayInput                    delaunay.h:46-57
  * The C++ shims with the reference's exact (mangled) signatures live in
  * surface-remesher_b200/csrc/srm_dropin.cpp (libsrm_dropin.so); INTEGRATION.md shows
  * how an unmodified main.cpp links against them.
@@ -75,6 +79,21 @@ int srm_seed(short *voronoi, const float *density, const unsigned char *mask, in
 /* generateMask (gcvt.h:143-159): mask[int((p-l)/scale)] = 1 for every constraint point (x,y pairs). */
 int srm_generate_mask(unsigned char *mask, const double *points_xy, int num_points, int n, double scale,
                       double left, double lower);
+
+/* locate (recover.h:63-83) for num_query points: face_out[q] = the FIRST face (index order) of the 2-D mesh in which
+ * all three barycentric weights of the point are >= 0, or -1; w_out (3 per query, may be NULL) = weights of the
+ * face's vertices 0,1,2.  mesh_xy: 2 doubles per vertex; faces: 3 vertex indices per face. */
+int srm_locate(const double *mesh_xy, int num_vertices, const int *faces, int num_faces, const double *query_xy,
+               int num_query, int *face_out, double *w_out);
+
+/* recover (recover.h:85-153): lift the CDT back to the surface.  mesh_xyz[v] = 3-D position of the surface vertex
+ * that 2-D mesh vertex v maps to (vertex_2d_to_3d).  points_xy = the CDT input points: first the free sites, then
+ * num_cpoints constraint points whose mesh vertices are cpoint_vertex[].  Output: one 3-D vertex per point (free
+ * sites: barycentric lift in their face; constraint points: their mesh vertex) and tri_keep[t] = 1 iff the centroid
+ * of CDT triangle t lies in a face of the 2-D mesh (the others are dropped, recover.h:134-136). */
+int srm_recover(const double *mesh_xy, const double *mesh_xyz, int num_vertices, const int *faces, int num_faces,
+                const double *points_xy, int num_points, const int *cpoint_vertex, int num_cpoints,
+                const int *cdt_tri, int num_cdt_tri, double *vertices_xyz, unsigned char *tri_keep, int *num_kept);
 
 /* ------------------------------------------------------------ handle API (device-resident state) */
 

@@ -473,6 +473,78 @@ void orc_rasterise(const double *pts, const double *wt, int num_point, const int
         }
 }
 
+/* ------------------------------------------------------- locate + lift (f3) */
+
+/* recover.h:30-53 `barycentric`, host arithmetic (no contraction: this file is built with -ffp-contract=off).
+ * w[0],w[1],w[2] = weights of p1,p2,p3 (the out-parameter rotation cancels, Appendix A6).  Returns 0 for a
+ * degenerate face (the reference sets all weights to -1, which the caller rejects). */
+static inline int rec_bary(double x1, double y1, double x2, double y2, double x3, double y3, double x0, double y0,
+                           double *w) {
+    double v0x = x2 - x1, v0y = y2 - y1, v1x = x3 - x1, v1y = y3 - y1, v2x = x0 - x1, v2y = y0 - y1;
+    double d00 = v0x * v0x + v0y * v0y, d01 = v0x * v1x + v0y * v1y, d11 = v1x * v1x + v1y * v1y;
+    double d20 = v2x * v0x + v2y * v0y, d21 = v2x * v1x + v2y * v1y;
+    double denom = d00 * d11 - d01 * d01;
+    if (denom == 0) return 0;
+    double w1 = (d11 * d20 - d01 * d21) / denom, w2 = (d00 * d21 - d01 * d20) / denom, w3 = 1.0 - w1 - w2;
+    w[0] = w3; w[1] = w1; w[2] = w2;
+    return 1;
+}
+
+/* recover.h:63-83 `locate`: the first face (index order) with all weights >= 0; -1 if none.  Brute force over
+ * every face, like the reference.  w (3 doubles) is written only on success. */
+int orc_locate_one(const double *pts, const int *tri, int T, double x, double y, double *w) {
+    for (int t = 0; t < T; ++t) {
+        int a = tri[3 * t], b = tri[3 * t + 1], c = tri[3 * t + 2];
+        double ww[3];
+        if (!rec_bary(pts[2 * a], pts[2 * a + 1], pts[2 * b], pts[2 * b + 1], pts[2 * c], pts[2 * c + 1], x, y, ww)) continue;
+        if (ww[0] < 0 || ww[1] < 0 || ww[2] < 0) continue;
+        if (w) { w[0] = ww[0]; w[1] = ww[1]; w[2] = ww[2]; }
+        return t;
+    }
+    return -1;
+}
+
+void orc_locate(const double *pts, const int *tri, int T, const double *qxy, int Q, int *face, double *w) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int q = 0; q < Q; ++q) {
+        double ww[3] = {0, 0, 0};
+        face[q] = orc_locate_one(pts, tri, T, qxy[2 * q], qxy[2 * q + 1], ww);
+        if (w) { w[3 * q] = ww[0]; w[3 * q + 1] = ww[1]; w[3 * q + 2] = ww[2]; }
+    }
+}
+
+/* recover.h:85-153 `recover` on plain arrays.  pts3d[v] = 3-D position that 2-D mesh vertex v maps to.
+ * points: nfree free sites followed by ncp constraint points (mesh vertices cpv[]).  A site in no face reuses
+ * the previous site's face and weights (f_loc is not reset, :92-96).  Returns the number of kept triangles,
+ * -1 if the first site lies in no face (the reference reads an uninitialised f_loc there). */
+int orc_recover(const double *pts, const double *pts3d, const int *tri, int T, const double *pxy, int npoints,
+                const int *cpv, int ncp, const int *cdt, int M, double *out, unsigned char *keep) {
+    int nfree = npoints - ncp, f = -1;
+    double w[3] = {0, 0, 0};
+    for (int i = 0; i < nfree; ++i) {
+        double ww[3];
+        int g = orc_locate_one(pts, tri, T, pxy[2 * i], pxy[2 * i + 1], ww);
+        if (g >= 0) { f = g; w[0] = ww[0]; w[1] = ww[1]; w[2] = ww[2]; }
+        if (f < 0) return -1;
+        for (int d = 0; d < 3; ++d) {
+            double s = 0.0;
+            for (int j = 0; j < 3; ++j) s += pts3d[3 * tri[3 * f + j] + d] * w[j];
+            out[3 * i + d] = s;
+        }
+    }
+    for (int i = 0; i < ncp; ++i)
+        for (int d = 0; d < 3; ++d) out[3 * (size_t)(nfree + i) + d] = pts3d[3 * (size_t)cpv[i] + d];
+    int kept = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : kept)
+    for (int t = 0; t < M; ++t) {
+        int a = cdt[3 * t], b = cdt[3 * t + 1], c = cdt[3 * t + 2];
+        double cx = (pxy[2 * a] + pxy[2 * b] + pxy[2 * c]) / 3.0, cy = (pxy[2 * a + 1] + pxy[2 * b + 1] + pxy[2 * c + 1]) / 3.0;
+        keep[t] = orc_locate_one(pts, tri, T, cx, cy, NULL) >= 0;
+        kept += keep[t];
+    }
+    return kept;
+}
+
 /* ----------------------------------------------- CPU baseline (bench.py only) */
 
 /* OpenMP Lloyd iteration used as BASELINE.md §4(b): separable exact labelling,

@@ -16,12 +16,14 @@ from .api import (  # noqa: F401
     generateMask,
     lib,
     lib_path,
+    locate,
     putConstrains,
     randomPoints,
+    recover,
     row_bands,
 )
 
 __all__ = [
     "MARKER", "Context", "SrmError", "centroidalVoronoi", "discretization_d", "gCVT", "generateMask",
-    "lib", "lib_path", "putConstrains", "randomPoints", "row_bands",
+    "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands",
 ]

@@ -49,6 +49,8 @@ def lib():
     L.srm_release_cache.argtypes = []
     L.srm_seed.argtypes = [p, p, p, i, i, p]
     L.srm_generate_mask.argtypes = [p, p, i, i, d, d, d]
+    L.srm_locate.argtypes = [p, i, p, i, p, i, p, p]
+    L.srm_recover.argtypes = [p, p, i, p, i, p, i, p, i, p, i, p, p, C.POINTER(i)]
     L.srm_create.argtypes = [C.POINTER(p), i, i, i, i]
     L.srm_destroy.argtypes = [p]
     L.srm_set_stream.argtypes = [p, p]
@@ -77,7 +79,7 @@ def lib():
     L.srm_debug_counts.argtypes = [p, C.POINTER(C.c_longlong), C.POINTER(i)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
-    for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_create", "srm_destroy",
+    for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
                  "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
@@ -161,6 +163,32 @@ def generateMask(points_xy, mask, imageSize, scale, l, b):
     pts = np.ascontiguousarray(points_xy, np.float64)
     _ck(lib().srm_generate_mask(_np(mask, np.uint8, (imageSize, imageSize)), _np(pts, np.float64), len(pts),
                                 int(imageSize), float(scale), float(l), float(b)))
+
+
+def locate(points_2d, faces, queries):
+    """recover.h:63-83 for an array of points: (face ids int32[Q] with -1 = in no face, weights float64[Q,3])."""
+    pts = np.ascontiguousarray(points_2d, np.float64); tri = np.ascontiguousarray(faces, np.int32)
+    q = np.ascontiguousarray(queries, np.float64)
+    face = np.empty(len(q), np.int32); w = np.zeros((len(q), 3))
+    _ck(lib().srm_locate(_np(pts, np.float64), len(pts), _np(tri, np.int32), len(tri), _np(q, np.float64), len(q),
+                         _np(face, np.int32), _np(w, np.float64)))
+    return face, w
+
+
+def recover(points_2d, points_3d, faces, points_xy, cpoint_vertex, cdt_triangles):
+    """recover.h:85-153 on arrays: points_3d[v] = surface position of 2-D mesh vertex v; points_xy = CDT input points
+    (free sites, then the constraint points, whose mesh vertices are cpoint_vertex); cdt_triangles index points_xy.
+    Returns (vertices float64[P,3], keep uint8[M]): the triangles with keep == 1 form the remeshed surface."""
+    pts = np.ascontiguousarray(points_2d, np.float64); p3 = np.ascontiguousarray(points_3d, np.float64)
+    tri = np.ascontiguousarray(faces, np.int32); q = np.ascontiguousarray(points_xy, np.float64)
+    cpv = np.ascontiguousarray(cpoint_vertex, np.int32); cdt = np.ascontiguousarray(cdt_triangles, np.int32)
+    out = np.zeros((len(q), 3)); keep = np.zeros(max(len(cdt), 1), np.uint8)
+    kept = C.c_int(0)
+    _ck(lib().srm_recover(_np(pts, np.float64), _np(p3, np.float64), len(pts), _np(tri, np.int32), len(tri),
+                          _np(q, np.float64), len(q), cpv.ctypes.data_as(C.c_void_p) if len(cpv) else None, len(cpv),
+                          cdt.ctypes.data_as(C.c_void_p) if len(cdt) else None, len(cdt), _np(out, np.float64),
+                          _np(keep, np.uint8), C.byref(kept)))
+    return out, keep[: len(cdt)]
 
 
 # ---------------------------------------------------------------- handle API

@@ -955,6 +955,112 @@ out:
     return rc;
 }
 
+// ------------------------------------------------------------------ locate + lift (recover.h:63-153)
+
+namespace {
+struct DevBufs {   // frees what it allocated when it goes out of scope
+    std::vector<void *> p;
+    ~DevBufs() { for (void *q : p) cudaFree(q); }
+    template <typename T> cudaError_t up(T **d, const T *h, size_t count) {
+        cudaError_t e = cudaMalloc((void **)d, sizeof(T) * (count ? count : 1));
+        if (e != cudaSuccess) return e;
+        p.push_back(*d);
+        return (h && count) ? cudaMemcpy(*d, h, sizeof(T) * count, cudaMemcpyHostToDevice) : cudaSuccess;
+    }
+};
+}  // namespace
+
+static int check_faces(const char *who, const int *faces, int num_faces, int num_vertices) {
+    for (int i = 0; i < 3 * num_faces; ++i)
+        if (faces[i] < 0 || faces[i] >= num_vertices) return fail(SRM_ERR_ARG, "%s: vertex index out of range", who);
+    return SRM_OK;
+}
+
+extern "C" int srm_locate(const double *mesh_xy, int num_vertices, const int *faces, int num_faces, const double *query_xy,
+                          int num_query, int *face_out, double *w_out) {
+    if (!mesh_xy || num_vertices <= 0 || (!faces && num_faces > 0) || num_faces < 0 || (!query_xy && num_query > 0) ||
+        num_query < 0 || !face_out)
+        return fail(SRM_ERR_ARG, "srm_locate: bad argument");
+    int rc = check_faces("srm_locate", faces, num_faces, num_vertices);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRM_ERR_CUDA, "srm_locate: no CUDA device (libsrm has no CPU fallback)");
+    DevBufs B;
+    double *dp = nullptr, *dq = nullptr, *dw = nullptr;
+    int *dt = nullptr, *df = nullptr;
+    SrmLocator *L = nullptr;
+    CK(B.up(&dp, mesh_xy, 2 * (size_t)num_vertices));
+    CK(B.up(&dt, faces, 3 * (size_t)num_faces));
+    CK(B.up(&dq, query_xy, 2 * (size_t)num_query));
+    CK(B.up(&df, (const int *)nullptr, (size_t)num_query));
+    CK(B.up(&dw, (const double *)nullptr, 3 * (size_t)num_query));
+    CK(srm_locator_build(nullptr, mesh_xy, num_vertices, dp, dt, num_faces, &L));
+    cudaError_t e = srm_locator_query(nullptr, L, dp, dt, dq, nullptr, num_query, df, dw);
+    if (e == cudaSuccess && num_query) e = cudaMemcpy(face_out, df, sizeof(int) * num_query, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && num_query && w_out) e = cudaMemcpy(w_out, dw, sizeof(double) * 3 * num_query, cudaMemcpyDeviceToHost);
+    srm_locator_free(L);
+    if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_locate: %s", cudaGetErrorString(e));
+    return SRM_OK;
+}
+
+extern "C" int srm_recover(const double *mesh_xy, const double *mesh_xyz, int num_vertices, const int *faces, int num_faces,
+                           const double *points_xy, int num_points, const int *cpoint_vertex, int num_cpoints,
+                           const int *cdt_tri, int num_cdt_tri, double *vertices_xyz, unsigned char *tri_keep,
+                           int *num_kept) {
+    if (!mesh_xy || !mesh_xyz || num_vertices <= 0 || (!faces && num_faces > 0) || num_faces < 0 || !points_xy ||
+        num_points < 0 || num_cpoints < 0 || num_cpoints > num_points || (!cpoint_vertex && num_cpoints > 0) ||
+        (!cdt_tri && num_cdt_tri > 0) || num_cdt_tri < 0 || !vertices_xyz || (!tri_keep && num_cdt_tri > 0))
+        return fail(SRM_ERR_ARG, "srm_recover: bad argument");
+    int rc = check_faces("srm_recover", faces, num_faces, num_vertices);
+    if (rc) return rc;
+    for (int i = 0; i < 3 * num_cdt_tri; ++i)
+        if (cdt_tri[i] < 0 || cdt_tri[i] >= num_points) return fail(SRM_ERR_ARG, "srm_recover: CDT vertex index out of range");
+    for (int i = 0; i < num_cpoints; ++i)
+        if (cpoint_vertex[i] < 0 || cpoint_vertex[i] >= num_vertices) return fail(SRM_ERR_ARG, "srm_recover: constraint vertex out of range");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SRM_ERR_CUDA, "srm_recover: no CUDA device (libsrm has no CPU fallback)");
+    const int nfree = num_points - num_cpoints;
+    DevBufs B;
+    double *dp = nullptr, *d3 = nullptr, *dq = nullptr, *dw = nullptr, *dout = nullptr;
+    int *dt = nullptr, *df = nullptr, *dc = nullptr, *dfc = nullptr;
+    SrmLocator *L = nullptr;
+    CK(B.up(&dp, mesh_xy, 2 * (size_t)num_vertices));
+    CK(B.up(&d3, mesh_xyz, 3 * (size_t)num_vertices));
+    CK(B.up(&dt, faces, 3 * (size_t)num_faces));
+    CK(B.up(&dq, points_xy, 2 * (size_t)num_points));
+    CK(B.up(&dc, cdt_tri, 3 * (size_t)num_cdt_tri));
+    CK(B.up(&df, (const int *)nullptr, (size_t)nfree));
+    CK(B.up(&dw, (const double *)nullptr, 3 * (size_t)nfree));
+    CK(B.up(&dout, (const double *)nullptr, 3 * (size_t)nfree));
+    CK(B.up(&dfc, (const int *)nullptr, (size_t)num_cdt_tri));
+    CK(srm_locator_build(nullptr, mesh_xy, num_vertices, dp, dt, num_faces, &L));
+    // sites: locate + barycentric lift (recover.h:94-109); CDT triangles: keep iff the centroid lies in a face (:115-142)
+    cudaError_t e = srm_locator_query(nullptr, L, dp, dt, dq, nullptr, nfree, df, dw);
+    if (e == cudaSuccess) e = srm_launch_lift(nullptr, dt, d3, df, dw, nfree, dout);
+    if (e == cudaSuccess) e = srm_locator_query(nullptr, L, dp, dt, dq, dc, num_cdt_tri, dfc, nullptr);
+    std::vector<int> hf((size_t)nfree), hfc((size_t)num_cdt_tri);
+    if (e == cudaSuccess && nfree) e = cudaMemcpy(vertices_xyz, dout, sizeof(double) * 3 * nfree, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && nfree) e = cudaMemcpy(hf.data(), df, sizeof(int) * nfree, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && num_cdt_tri) e = cudaMemcpy(hfc.data(), dfc, sizeof(int) * num_cdt_tri, cudaMemcpyDeviceToHost);
+    srm_locator_free(L);
+    if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_recover: %s", cudaGetErrorString(e));
+    // A site that lies in no face: the reference ignores locate's return value and lifts with the PREVIOUS site's
+    // face and weights (f_loc is not reset, recover.h:92-96), i.e. repeats the previous vertex.
+    for (int i = 0; i < nfree; ++i)
+        if (hf[i] < 0) {
+            if (i == 0) return fail(SRM_ERR_ARG, "srm_recover: the first site lies in no face of the mesh");
+            for (int d = 0; d < 3; ++d) vertices_xyz[3 * i + d] = vertices_xyz[3 * (i - 1) + d];
+        }
+    for (int i = 0; i < num_cpoints; ++i)   // constraint points keep their mesh vertex (recover.h:111-113)
+        for (int d = 0; d < 3; ++d) vertices_xyz[3 * (size_t)(nfree + i) + d] = mesh_xyz[3 * (size_t)cpoint_vertex[i] + d];
+    int kept = 0;
+    for (int i = 0; i < num_cdt_tri; ++i) { tri_keep[i] = hfc[i] >= 0; kept += tri_keep[i]; }
+    if (num_kept) *num_kept = kept;
+    return SRM_OK;
+}
+
 // putConstrains + randomPoints (gcvt.h:58-122).  Host code in the reference too; the RNG is the
 // never-seeded KISS generator, which degenerates to the LCG j <- 69069 j + 1234567 on 64-bit
 // unsigned long.  Attempts are capped so that an unsatisfiable request fails

@@ -112,5 +112,15 @@ void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value);
 void srm_launch_density_scale(cudaStream_t st, const float *in, float *out, int s);
 void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K);
 
+// point location + lift (srm_recover.cu; recover.h:63-153)
+struct SrmLocator;
+cudaError_t srm_locator_build(cudaStream_t st, const double *pts_host, int P, const double *pts_dev, const int *tri_dev,
+                              int T, SrmLocator **out);
+void srm_locator_free(SrmLocator *L);
+cudaError_t srm_locator_query(cudaStream_t st, const SrmLocator *L, const double *pts_dev, const int *tri_dev,
+                              const double *qxy_dev, const int *centroid_of_dev, int Q, int *face_dev, double *w_dev);
+cudaError_t srm_launch_lift(cudaStream_t st, const int *tri_dev, const double *pts3d_dev, const int *face_dev,
+                            const double *w_dev, int Q, double *out_dev);
+
 cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int num_point, const int *tri, int num_tri,
                        float *density, double scale, int n);

@@ -48,6 +48,9 @@ def lib():
         L.orc_zoom_in.argtypes = [p, p, C.c_int]
         L.orc_gcvt_multires.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, p, p, p]
         L.orc_gcvt_multires.restype = C.c_int
+        L.orc_locate.argtypes = [p, p, C.c_int, p, C.c_int, p, p]
+        L.orc_recover.argtypes = [p, p, p, C.c_int, p, C.c_int, p, C.c_int, p, C.c_int, p, p]
+        L.orc_recover.restype = C.c_int
         L.orc_rasterise.argtypes = [p, p, C.c_int, p, C.c_int, p, C.c_double, C.c_int]
         L.orc_fast_scratch_bytes.argtypes = [C.c_int, C.c_int]
         L.orc_fast_scratch_bytes.restype = C.c_size_t
@@ -176,6 +179,26 @@ def gcvt_multires(coarse_seeds, density, mask, depth, max_iter, stop_rule=1):
     while nl < dd and (n >> nl) >= 256:
         nl += 1
     return vor, it, li[:nl].tolist(), float(om[0]), float(en[0])
+
+
+def locate(points, triangles, queries):
+    """recover.h locate, brute force: (face ids int32[Q], weights float64[Q,3])."""
+    pts = np.ascontiguousarray(points, np.float64); tri = np.ascontiguousarray(triangles, np.int32)
+    q = np.ascontiguousarray(queries, np.float64)
+    face = np.empty(len(q), np.int32); w = np.zeros((len(q), 3))
+    lib().orc_locate(_p(pts), _p(tri), len(tri), _p(q), len(q), _p(face), _p(w))
+    return face, w
+
+
+def recover(points, points3d, triangles, pxy, cpoint_vertex, cdt_tri):
+    """recover.h recover on arrays: (vertices float64[P,3], keep uint8[M], kept)."""
+    pts = np.ascontiguousarray(points, np.float64); p3 = np.ascontiguousarray(points3d, np.float64)
+    tri = np.ascontiguousarray(triangles, np.int32); q = np.ascontiguousarray(pxy, np.float64)
+    cpv = np.ascontiguousarray(cpoint_vertex, np.int32); cdt = np.ascontiguousarray(cdt_tri, np.int32)
+    out = np.zeros((len(q), 3)); keep = np.zeros(len(cdt), np.uint8)
+    kept = lib().orc_recover(_p(pts), _p(p3), _p(tri), len(tri), _p(q), len(q), _p(cpv), len(cpv), _p(cdt), len(cdt),
+                             _p(out), _p(keep))
+    return out, keep, kept
 
 
 def rasterise(points, weight, triangles, scale, n):
