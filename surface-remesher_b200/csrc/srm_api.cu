@@ -98,6 +98,7 @@ struct srm_ctx {
     int2 *rle = nullptr;
     int *rle_cnt = nullptr, *idmap = nullptr, *claim = nullptr, *labels = nullptr, *scratch_map = nullptr;
     int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
+    int *edge = nullptr;       // row bands: per column, nearest site row above / below the band (2n ints)
     int dbg_stats = 0;
     bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
     SrmCtl *ctl = nullptr;
@@ -197,6 +198,7 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
+    CKD(cudaMalloc(&c->edge, 2 * (size_t)n * sizeof(int)));
     CKD(cudaMalloc(&c->idmap, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->claim, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
@@ -225,7 +227,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
     if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
-                    c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->idmap, c->claim, c->labels,
+                    c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->edge, c->idmap, c->claim, c->labels,
                     c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -546,8 +548,8 @@ extern "C" int srm_set_omega(srm_ctx *c, float omega) {
 static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy) {
     const int buf = it & 1;
     double *acc = cur_acc(c, it);
-    srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop);
-    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1);
+    srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop, c->g.row0, c->g.row1, c->edge);
+    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1, c->edge);
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
         CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
@@ -671,8 +673,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         cudaEvent_t *e = &ev[(size_t)i * 6];
         CK(cudaEventRecord(e[0], c->stream));
         double *acc = cur_acc(c, it);
-        srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1);
-        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1, c->g.row0, c->g.row1);
+        srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1, c->g.row0, c->g.row1, c->edge);
+        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1, c->g.row0, c->g.row1, c->edge);
         CK(cudaEventRecord(e[1], c->stream));
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {

@@ -36,13 +36,20 @@ struct Col8 {          // 8 consecutive columns of one band
     int M;             // min over the 8 columns of the upper bound gmax
 };
 
+struct Raw8 { uint4 w0, w1, u4, d4; };   // 8 columns of one word row: bitmap words + up / dn carries (64 B)
+
+__device__ __forceinline__ Raw8 load_raw8(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                          const short *__restrict__ dn, size_t o) {
+    Raw8 r;
+    r.w0 = *reinterpret_cast<const uint4 *>(bits + o); r.w1 = *reinterpret_cast<const uint4 *>(bits + o + 4);
+    r.u4 = *reinterpret_cast<const uint4 *>(up + o); r.d4 = *reinterpret_cast<const uint4 *>(dn + o);
+    return r;
+}
+
 template <int R>
-__device__ __forceinline__ void load_col8(const uint32_t *__restrict__ bits, const short *__restrict__ up,
-                                          const short *__restrict__ dn, size_t o, int j, int k0, int Y0, Col8 &c) {
-    const uint4 w0 = *reinterpret_cast<const uint4 *>(bits + o), w1 = *reinterpret_cast<const uint4 *>(bits + o + 4);
-    const uint4 u4 = *reinterpret_cast<const uint4 *>(up + o), d4 = *reinterpret_cast<const uint4 *>(dn + o);
-    const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    const uint32_t uu[4] = {u4.x, u4.y, u4.z, u4.w}, dd[4] = {d4.x, d4.y, d4.z, d4.w};
+__device__ __forceinline__ void unpack_col8(const Raw8 &r, int j, int k0, int Y0, Col8 &c) {
+    const uint32_t w[8] = {r.w0.x, r.w0.y, r.w0.z, r.w0.w, r.w1.x, r.w1.y, r.w1.z, r.w1.w};
+    const uint32_t uu[4] = {r.u4.x, r.u4.y, r.u4.z, r.u4.w}, dd[4] = {r.d4.x, r.d4.y, r.d4.z, r.d4.w};
     const uint32_t rmask = (R == 32) ? 0xffffffffu : ((1u << R) - 1u);
     c.M = SRM_BIG;
 #pragma unroll
@@ -63,6 +70,12 @@ __device__ __forceinline__ void load_col8(const uint32_t *__restrict__ bits, con
         c.U[k] = U; c.D[k] = D; c.inb[k] = in; c.gmin[k] = gmin;
         c.M = min(c.M, gmax);
     }
+}
+
+template <int R>
+__device__ __forceinline__ void load_col8(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+                                          const short *__restrict__ dn, size_t o, int j, int k0, int Y0, Col8 &c) {
+    unpack_col8<R>(load_raw8(bits, up, dn, o), j, k0, Y0, c);
 }
 
 template <int R>
@@ -197,7 +210,7 @@ __device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v,
 #define PROF_CNT(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(v)); } while (0)
 
 template <int RPW, int C, int GS0, int GS1>
-__global__ void __launch_bounds__(BAND_NT) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+__global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
                                                   const short *__restrict__ dn, int n, int row0, int CL,
                                                   int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,

@@ -77,9 +77,9 @@ struct SrmGrid {           // geometry of one context
 };
 
 void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
-                     int *claim, int respect_stop);
+                     int *claim, int respect_stop, int row0, int row1, int *edge);
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop, int row0, int row1);
+                      int respect_stop, int row0, int row1, const int *edge);
 // fused fast path (srm_band.cu)
 cudaError_t srm_band_setup(int n);
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,

@@ -19,8 +19,14 @@
 
 // ------------------------------------------------------------------ sites -> bitmap
 
+// Row-band contexts fill only their own word rows of the bitmap; what lies outside the band enters through two
+// per-column edge values (the nearest site row above / below the band), which seed the band's carry scan.  This is
+// what kernelPropagateInterband (gcvt.cu:121-170) hands from band to band, here straight from the replicated site list.
+#define EDGE_NONE_TOP ((int)0x80808080)   // byte pattern of the per-iteration memset: "no site above" (< 0)
+#define EDGE_NONE_BOT ((int)0x7f7f7f7f)   // "no site below" (> 32767)
+
 __global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32_t *bits, int *idmap, int *claim,
-                       int respect_stop) {
+                       int respect_stop, int row0, int row1, int *edge) {
     if (respect_stop && ctl->stop) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ovf = 0;  // rows the band kernel hands to the robust path
     int id = blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,40 +34,56 @@ __global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32
     int p = sites[id];
     if (p == SRM_SENT) return;  // merged away
     int x = srm_x(p), y = srm_y(p);
-    atomicOr(&bits[(size_t)(y >> 5) * n + x], 1u << (y & 31));
+    if (y >= row0 && y < row1) atomicOr(&bits[(size_t)(y >> 5) * n + x], 1u << (y & 31));
+    else if (y < row0) atomicMax(&edge[x], y);
+    else atomicMin(&edge[n + x], y);
     size_t i = (size_t)y * n + x;
     idmap[i] = id;      // site pixel -> accumulator slot
     claim[i] = INT_MAX; // reset the dedupe claim left by the previous update
 }
 
 void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
-                     int *claim, int respect_stop) {
-    // the memset is skipped after a stop only in effect (bits are then unused until the final labelling
-    // rebuilds them), so it can stay unconditional
-    cudaMemsetAsync(bits, 0, (size_t)(n >> 5) * n * sizeof(uint32_t), st);
-    k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop);
+                     int *claim, int respect_stop, int row0, int row1, int *edge) {
+    // the memsets are skipped after a stop only in effect (bits are then unused until the final labelling
+    // rebuilds them), so they can stay unconditional
+    cudaMemsetAsync(bits + (size_t)(row0 >> 5) * n, 0, (size_t)((row1 - row0) >> 5) * n * sizeof(uint32_t), st);
+    if (row0 > 0 || row1 < n) {
+        cudaMemsetAsync(edge, 0x80, (size_t)n * sizeof(int), st);
+        cudaMemsetAsync(edge + n, 0x7f, (size_t)n * sizeof(int), st);
+    }
+    k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop, row0, row1, edge);
+}
+
+__device__ __forceinline__ int edge_top(const int *edge, int x) {
+    if (!edge) return SRM_MARK;
+    const int v = edge[x];
+    return v < 0 ? SRM_MARK : v;
+}
+__device__ __forceinline__ int edge_bot(const int *edge, int n, int x) {
+    if (!edge) return SRM_MARK;
+    const int v = edge[n + x];
+    return v > 32767 ? SRM_MARK : v;
 }
 
 // Generic form (any n): one thread per column, one sweep per direction.
 __global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__restrict__ up, short *__restrict__ dn,
-                        const SrmCtl *__restrict__ ctl, int respect_stop) {
+                        const SrmCtl *__restrict__ ctl, int respect_stop, int jbeg, int jend, const int *edge) {
     if (respect_stop && ctl->stop) return;
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
-    int nw = n >> 5;
     if (blockIdx.y == 0) {
-        int last = SRM_MARK;
+        int last = edge_top(edge, x);
 #pragma unroll 8
-        for (int j = 0; j < nw; ++j) {
+        for (int j = jbeg; j < jend; ++j) {
             size_t o = (size_t)j * n + x;
             uint32_t w = bits[o];
             up[o] = (short)last;
             if (w) last = 32 * j + 31 - __clz(w);
         }
     } else {
-        int next = SRM_MARK;
+        int next = edge_bot(edge, n, x);
 #pragma unroll 8
-        for (int j = nw - 1; j >= 0; --j) {
+        for (int j = jend - 1; j >= jbeg; --j) {
             size_t o = (size_t)j * n + x;
             uint32_t w = bits[o];
             dn[o] = (short)next;
@@ -80,11 +102,11 @@ __global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__r
 template <int WPS>  // words per segment held in registers
 __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up,
                                                           short *__restrict__ dn, const SrmCtl *__restrict__ ctl,
-                                                          int respect_stop) {
+                                                          int respect_stop, int jbeg, const int *edge) {
     __shared__ short s_last[CARRY_SEG][32], s_first[CARRY_SEG][32];
     if (respect_stop && ctl->stop) return;
     const int x = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
-    const int j0 = seg * WPS;
+    const int j0 = jbeg + seg * WPS;
     uint32_t w[WPS];
     int last = SRM_MARK, first = SRM_MARK;
 #pragma unroll
@@ -98,7 +120,7 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
     s_last[seg][threadIdx.x] = (short)last;
     s_first[seg][threadIdx.x] = (short)first;
     __syncthreads();
-    int cu = SRM_MARK, cd = SRM_MARK;  // nearest site row above / below this segment
+    int cu = edge_top(edge, x), cd = edge_bot(edge, n, x);  // nearest site row above / below this segment
     for (int q = 0; q < seg; ++q) { const int v = s_last[q][threadIdx.x]; if (v != SRM_MARK) cu = v; }
     for (int q = CARRY_SEG - 1; q > seg; --q) { const int v = s_first[q][threadIdx.x]; if (v != SRM_MARK) cd = v; }
 #pragma unroll
@@ -114,24 +136,20 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
 }
 
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop, int row0, int row1) {
-    // (A band-restricted scan — one thread per column walking outward from the band — was measured at 69 us against
-    // 12 us for this segmented full-column scan: too little parallelism, dependent loads.  All ranks scan everything.)
-    (void)row0; (void)row1;
+                      int respect_stop, int row0, int row1, const int *edge) {
+    // Carries of the band's own word rows only; the rest of the column is summarised by the edge values that k_bits
+    // collected (whole-grid contexts: no edges).  8 segments per column, words in registers.
+    const int jbeg = row0 >> 5, jend = row1 >> 5, nw = jend - jbeg;
+    const int *e = (row0 > 0 || row1 < n) ? edge : nullptr;
     dim3 grid(n / 32), block(32, CARRY_SEG);
-    const int wps = (n >> 5) / CARRY_SEG;  // n multiple of 256 -> integral
+    const int wps = (nw % CARRY_SEG) ? 0 : nw / CARRY_SEG;
+#define CARRY_CASE(W) case W: k_carry<W><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); break;
     switch (wps) {
-        case 1: k_carry<1><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 2: k_carry<2><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 3: k_carry<3><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 4: k_carry<4><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 8: k_carry<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 16: k_carry<16><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 32: k_carry<32><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 64: k_carry<64><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        case 128: k_carry<128><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
-        default: k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop); break;
+        CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
+        CARRY_CASE(64) CARRY_CASE(128)
+        default: k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e); break;
     }
+#undef CARRY_CASE
 }
 
 // ------------------------------------------------------------------ robust row path (fallback)

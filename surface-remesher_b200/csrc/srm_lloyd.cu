@@ -184,16 +184,35 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
     if (!(mask && mask[(size_t)ty * n + tx])) {
         double sW = 0, sX = 0, sY = 0;
         if (peers.world > 1) {
-            for (int q = 0; q < peers.world; ++q) {
-                // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
-                // cell spans one or two bands, so only those ranks' sums are pulled over NVLink
-                const double *base = peers.acc[q] + (size_t)peers.parity * peers.stride;
-                const unsigned char *tq = reinterpret_cast<const unsigned char *>(base + 4 * (size_t)peers.kcap + 4);
-                if (__ldcv(tq + id)) {
-                    const double *a = base + 4 * (size_t)id;
-                    const double2 wx = __ldcv(reinterpret_cast<const double2 *>(a));
-                    sW += wx.x; sX += wx.y; sY += __ldcv(a + 2);
+            // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
+            // cell spans one or two bands, so only those ranks' sums are pulled over NVLink.  Remote loads cost
+            // ~2 us each, so they are issued in independent batches of 8 ranks (all "touched" bytes, then all sums)
+            // and added in rank order (the same order on every rank: bit-identical totals).
+            for (int q0 = 0; q0 < peers.world; q0 += 8) {
+                const double *base[8];
+                unsigned char tch[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int q = min(q0 + k, peers.world - 1);
+                    base[k] = peers.acc[q] + (size_t)peers.parity * peers.stride;
+                    tch[k] = (q0 + k < peers.world)
+                                 ? __ldcv(reinterpret_cast<const unsigned char *>(base[k] + 4 * (size_t)peers.kcap + 4) + id)
+                                 : (unsigned char)0;
                 }
+                double2 wx[8];
+                double yy[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    wx[k] = make_double2(0, 0); yy[k] = 0;
+                    if (tch[k]) {
+                        const double *a = base[k] + 4 * (size_t)id;
+                        wx[k] = __ldcv(reinterpret_cast<const double2 *>(a));
+                        yy[k] = __ldcv(a + 2);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (tch[k]) { sW += wx[k].x; sX += wx[k].y; sY += yy[k]; }
             }
         } else {
             const double *a = acc + 4 * (size_t)id;
@@ -243,24 +262,32 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
         is_last = atomicAdd(&ctl->ticket, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
+    if (!is_last || threadIdx.x >= 32) return;   // the first warp of the last block runs the control
     __threadfence();
-    ctl->nlive = atomicExch(&ctl->live_acc, 0);
-    ctl->ticket = 0;
+    const int lane = threadIdx.x;
     if (peers.world > 1) {
         if (want_energy) {
+            // one remote load per lane, then a sum in rank order (identical on every rank)
             double e = 0;
-            for (int q = 0; q < peers.world; ++q) e += __ldcv(peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)Kcap);
-            ctl->E = (float)(e / ((double)n * (double)n)) * ctl->escale;
+            for (int q0 = 0; q0 < peers.world; q0 += 32) {
+                const int q = q0 + lane;
+                const double eq = (q < peers.world) ? __ldcv(peers.acc[q] + (size_t)peers.parity * peers.stride + 4 * (size_t)Kcap) : 0.0;
+                const int cnt = min(32, peers.world - q0);
+                for (int k = 0; k < cnt; ++k) e += __shfl_sync(0xffffffffu, eq, k);
+            }
+            if (lane == 0) ctl->E = (float)(e / ((double)n * (double)n)) * ctl->escale;
         }
-        acc[(size_t)(peers.parity ^ 1) * peers.stride + 4 * (size_t)Kcap] = 0;
-    } else {
+        if (lane == 0) acc[(size_t)(peers.parity ^ 1) * peers.stride + 4 * (size_t)Kcap] = 0;
+    } else if (lane == 0) {
         double *acc_energy = acc + 4 * (size_t)Kcap;
         if (want_energy) {
             ctl->E = (float)(acc_energy[0] / ((double)n * (double)n)) * ctl->escale;  // * powf(2, 2 level), gcvt.cu:1082
             acc_energy[0] = 0;
         }
     }
+    if (lane != 0) return;
+    ctl->nlive = atomicExch(&ctl->live_acc, 0);
+    ctl->ticket = 0;
     const int it = ctl->it + 1;
     ctl->it = it;
     if (it % 10 == 0) {

@@ -19,7 +19,7 @@ for N in ${SCALE_NS:-8 4}; do
 done
 MEM=$(free -g | awk '/Mem:/{print $7}')
 if [ "${SKIP_C4:-0}" = "0" ] && [ "$MEM" -gt 250 ]; then
-  timeout 600 $TR --nproc-per-node $NG --master-port 29540 bench.py --gpus $NG --n 32768 --sites 1000000 --steps 60 --warmup 6 --e2e-iters 10 --no-cpu > $OUT/bench_s2_c4_n${NG}.json 2> $OUT/bench_s2_c4_n${NG}.err
+  timeout 600 $TR --nproc-per-node $NG --master-port 29540 bench.py --gpus $NG --grid 32768 --sites 1000000 --steps 60 --warmup 6 --e2e-iters 10 --no-cpu > $OUT/bench_s2_c4_n${NG}.json 2> $OUT/bench_s2_c4_n${NG}.err
   echo "C4 N=$NG rc=$?"; head -c 400 $OUT/bench_s2_c4_n${NG}.json; echo
 else
   echo "C4 skipped (free host memory ${MEM} GB)"
