@@ -457,14 +457,17 @@ __global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict_
 
 // Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62.  Rows of an n-wide grid with the
 // BASELINE site densities have ~n/26 runs (316 at 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
-static int band_bufcap(int n) { return n <= 8192 ? 1024 : n <= 16384 ? 1536 : 3072; }
+static int band_bufcap(int n) { return n <= 8192 ? 1024 : n <= 16384 ? 1280 : 1792; }
 
 static int band_cap(int n) {
-    // Band-list capacity.  Measured on C3-like inputs: band list <= ~0.28 n entries.
-    //   n <=  8192: 2816 entries -> 4 CTAs/SM (22 KB list + 1 KB masks + 32 KB element buffers + static/system)
-    //   n <= 16384: 6144 entries -> 2 CTAs/SM;   n <= 32768: 12288 entries -> 1 CTA/SM
+    // Band-list capacity.  Measured on C3-like inputs with the 3-block pruning: band list mean 0.11 n, max
+    // 0.19 n entries.  Capacities are chosen for CTAs per SM (the kernel is latency bound, resident warps are what count):
+    //   n <=  8192: 2816 entries -> 55 KB  -> 4 CTAs/SM (the register file allows no more)
+    //   n <= 16384: 3584 entries -> 70 KB  -> 3 CTAs/SM
+    //   n <= 32768: 6144 entries -> 108 KB -> 2 CTAs/SM
+    // A band or row that exceeds them goes to the robust path (k_row), which has worst-case capacity.
     int cl = (3 * n) / 8;
-    const int cap = n <= 8192 ? 2816 : n <= 16384 ? 6144 : 12288;
+    const int cap = n <= 8192 ? 2816 : n <= 16384 ? 3584 : 6144;
     if (cl > cap) cl = cap;
     if (cl < 512) cl = 512;
     return cl;
@@ -487,10 +490,10 @@ cudaError_t srm_band_setup(int n) {
               s32 = (int)band_smem(32768, band_cap(32768));
     cudaError_t e = band_setup_one<1, 1024>(s8);
     if (e == cudaSuccess) e = band_setup_one<2, 1024>(s8);
-    if (e == cudaSuccess) e = band_setup_one<1, 1536>(s16);
-    if (e == cudaSuccess) e = band_setup_one<2, 1536>(s16);
-    if (e == cudaSuccess) e = band_setup_one<1, 3072>(s32);
-    if (e == cudaSuccess) e = band_setup_one<2, 3072>(s32);
+    if (e == cudaSuccess) e = band_setup_one<1, 1280>(s16);
+    if (e == cudaSuccess) e = band_setup_one<2, 1280>(s16);
+    if (e == cudaSuccess) e = band_setup_one<1, 1792>(s32);
+    if (e == cudaSuccess) e = band_setup_one<2, 1792>(s32);
     return e;
 }
 
@@ -524,8 +527,8 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
 #define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop, dbg
     if (C == 1024) { if (rpw == 1) band_launch_one<1, 1024>(BAND_ARGS); else band_launch_one<2, 1024>(BAND_ARGS); }
-    else if (C == 1536) { if (rpw == 1) band_launch_one<1, 1536>(BAND_ARGS); else band_launch_one<2, 1536>(BAND_ARGS); }
-    else { if (rpw == 1) band_launch_one<1, 3072>(BAND_ARGS); else band_launch_one<2, 3072>(BAND_ARGS); }
+    else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
+    else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }
 #undef BAND_ARGS
     return cudaGetLastError();
 }
