@@ -98,8 +98,8 @@ __global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__r
 // A CTA owns 32 columns; its 8 warps own 8 segments of the column's word-rows.  Each thread scans its
 // segment once (words kept in registers), segment summaries meet in shared memory, then the thread
 // writes both carries of its words.
-#define CARRY_SEG 8
-template <int WPS>  // words per segment held in registers
+// WPS words per segment are held in registers (<= 32: more spills), CARRY_SEG = 8, 16 or 32 segments per column.
+template <int WPS, int CARRY_SEG>
 __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up,
                                                           short *__restrict__ dn, const SrmCtl *__restrict__ ctl,
                                                           int respect_stop, int jbeg, const int *edge) {
@@ -135,20 +135,64 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
     }
 }
 
+// Same result without a register-resident segment: every thread walks its segment three times (summary, up
+// carries, down carries; the re-reads hit L2).  For long columns (n > 8192 on one GPU), where 32+ words per thread
+// would spill: 32 segments of nw/32 words.
+template <int CARRY_SEG>
+__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry_loop(const uint32_t *__restrict__ bits, int n,
+                                                               short *__restrict__ up, short *__restrict__ dn,
+                                                               const SrmCtl *__restrict__ ctl, int respect_stop,
+                                                               int jbeg, int wps, const int *edge) {
+    __shared__ short s_last[CARRY_SEG][32], s_first[CARRY_SEG][32];
+    if (respect_stop && ctl->stop) return;
+    const int x = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
+    const int j0 = jbeg + seg * wps;
+    int last = SRM_MARK, first = SRM_MARK;
+#pragma unroll 4
+    for (int k = 0; k < wps; ++k) {
+        const uint32_t w = bits[(size_t)(j0 + k) * n + x];
+        if (w) {
+            last = 32 * (j0 + k) + 31 - __clz(w);
+            if (first == SRM_MARK) first = 32 * (j0 + k) + __ffs(w) - 1;
+        }
+    }
+    s_last[seg][threadIdx.x] = (short)last;
+    s_first[seg][threadIdx.x] = (short)first;
+    __syncthreads();
+    int cu = edge_top(edge, x), cd = edge_bot(edge, n, x);
+    for (int q = 0; q < seg; ++q) { const int v = s_last[q][threadIdx.x]; if (v != SRM_MARK) cu = v; }
+    for (int q = CARRY_SEG - 1; q > seg; --q) { const int v = s_first[q][threadIdx.x]; if (v != SRM_MARK) cd = v; }
+#pragma unroll 4
+    for (int k = 0; k < wps; ++k) {
+        const size_t o = (size_t)(j0 + k) * n + x;
+        const uint32_t w = bits[o];
+        up[o] = (short)cu;
+        if (w) cu = 32 * (j0 + k) + 31 - __clz(w);
+    }
+#pragma unroll 4
+    for (int k = wps - 1; k >= 0; --k) {
+        const size_t o = (size_t)(j0 + k) * n + x;
+        const uint32_t w = bits[o];
+        dn[o] = (short)cd;
+        if (w) cd = 32 * (j0 + k) + __ffs(w) - 1;
+    }
+}
+
 void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
                       int respect_stop, int row0, int row1, const int *edge) {
     // Carries of the band's own word rows only; the rest of the column is summarised by the edge values that k_bits
     // collected (whole-grid contexts: no edges).  8 segments per column, words in registers.
     const int jbeg = row0 >> 5, jend = row1 >> 5, nw = jend - jbeg;
     const int *e = (row0 > 0 || row1 < n) ? edge : nullptr;
-    dim3 grid(n / 32), block(32, CARRY_SEG);
-    const int wps = (nw % CARRY_SEG) ? 0 : nw / CARRY_SEG;
-#define CARRY_CASE(W) case W: k_carry<W><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); break;
-    switch (wps) {
-        CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
-        CARRY_CASE(64) CARRY_CASE(128)
-        default: k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e); break;
+    const int wps = (nw % 8) ? 0 : nw / 8;
+    dim3 grid(n / 32), block(32, 8);
+    if (wps > 32 && nw % 32 == 0) {   // long columns: 32 segments, looped
+        k_carry_loop<32><<<grid, dim3(32, 32), 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, nw / 32, e);
+        return;
     }
+#define CARRY_CASE(W) if (wps == W) { k_carry<W, 8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); return; }
+    CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
+    k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e);
 #undef CARRY_CASE
 }
 
