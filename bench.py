@@ -155,11 +155,14 @@ def run_ours(args):
     n, k, K, W = args.n, args.sites, args.steps, args.warmup
     pinned = n <= 16384   # 32768^2: 9.7 GB of host buffers per rank stay pageable (8 ranks would pin 77 GB)
     dens, mask, vor = make_inputs(n, k, pinned=pinned)
-    r0, r1 = S.row_bands(n, world)[rank]
+    # row bands of equal work (sites per block of rows), from the replicated seed map: identical on every rank
+    bands = S.row_bands_balanced(n, world, np.nonzero(vor[..., 0] != -32768)[0]) if args.bands == "balanced" \
+        else S.row_bands(n, world)
+    r0, r1 = bands[rank]
 
     eng = CudaBandEngine(n, r0, r1, local)
     eng.set_inputs(dens, mask, vor)
-    sl = ShardedLloyd(n, rank, world, eng, dist if world > 1 else None)
+    sl = ShardedLloyd(n, rank, world, eng, dist if world > 1 else None, bands)
     if world > 1 and args.collective != "py":
         sl.bind_native_collective(args.collective)   # all-reduce inside libsrm's C++ loop (peer memory or NCCL)
 
@@ -222,7 +225,7 @@ def run_ours(args):
         # the site-indexed buffers across calls of the same size, so the mappings stay valid for the timed call
         eng2 = CudaBandEngine(n, r0, r1, local)
         eng2.set_inputs(dens, mask, vor)
-        sl2 = ShardedLloyd(n, rank, world, eng2, dist)
+        sl2 = ShardedLloyd(n, rank, world, eng2, dist, bands)
         if args.collective != "py":
             sl2.bind_native_collective(args.collective)
         barrier()
@@ -252,7 +255,7 @@ def run_ours(args):
         "dtype": "int32 labels / f64 accumulators", "data": "synthetic",
         "config": {"workload": f"C3 curvature-like anisotropic density {n}x{n}, {k} sites + {int(mask.sum())} fixed boundary sites "
                                f"(BASELINE.json {'configs[2]' if n == 8192 else 'configs[3]' if n == 32768 else 'generator of configs[2], other size'})", "grid": n, "sites": st["num_sites"],
-                   "parallelism": f"row bands x{world}, collective={args.collective}" if world > 1 else "single GPU",
+                   "parallelism": f"row bands x{world} ({args.bands}: {[b[1] - b[0] for b in bands]} rows), collective={args.collective}" if world > 1 else "single GPU",
                    "l2": "fp64 prefix arrays (24 B/px, read at run ends) + site-id map (4 B/px, read per run) "
                          f"= {28 * N / 1e6:.0f} MB > 126 MB L2; no explicit flush",
                    "stop_rule": "off (fixed step count); energy every 10th step like the reference"},
@@ -380,6 +383,8 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl", "py"],
                     help="N>1: p2p = fused all-reduce over peer memory inside the update kernel (default); nccl = NCCL "
                          "all-reduce issued by libsrm; py = torch.distributed all-reduce per step from Python")
+    ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
+                    help="N>1: row bands of equal work (sites per block of rows; default) or of equal height")
     ap.add_argument("--_ref_child", action="store_true")
     ap.add_argument("--_inputs", default=None)
     args = ap.parse_args()

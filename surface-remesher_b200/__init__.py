@@ -21,9 +21,10 @@ from .api import (  # noqa: F401
     randomPoints,
     recover,
     row_bands,
+    row_bands_balanced,
 )
 
 __all__ = [
     "MARKER", "Context", "SrmError", "centroidalVoronoi", "discretization_d", "gCVT", "generateMask",
-    "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands",
+    "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands", "row_bands_balanced",
 ]

@@ -201,6 +201,38 @@ def row_bands(n, world):
     return [(r * h, (r + 1) * h) for r in range(world)]
 
 
+def row_bands_balanced(n, world, site_rows, unit=None, fixed=0.3):
+    """Row bands of roughly equal WORK instead of equal height.  The band kernel's time per row follows the number
+    of sites near the row (band-list and envelope sizes) plus a fixed part (Phase A scans every column), so on
+    densities with empty regions equal-height bands leave the ranks of the dense rows as stragglers (C3 on 8 ranks:
+    1.8x the mean number of sites in the middle bands, 0.1x at the top and bottom).  Weight of a `unit`-row block =
+    sites in the block + `fixed` x the mean; boundaries are multiples of `unit` rows (default: 256 = whole carry
+    segments for n >= 16384, 64 below).
+    Deterministic in its inputs: every rank computes the same partition from the replicated site map.
+    site_rows: y coordinates of the sites."""
+    if world == 1:
+        return [(0, n)]
+    if unit is None:
+        unit = 256 if n >= 16384 else 64
+    if n % unit or n // unit < world:
+        return row_bands(n, world)
+    nb = n // unit
+    hist = np.bincount(np.asarray(site_rows, np.int64) // unit, minlength=nb)[:nb].astype(np.float64)
+    w = hist + fixed * max(hist.mean(), 1e-9)
+    cum = np.concatenate([[0.0], np.cumsum(w)])
+    cuts = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        i = int(np.searchsorted(cum, target))
+        if i > 0 and abs(cum[i - 1] - target) <= abs(cum[min(i, nb)] - target):
+            i -= 1
+        i = max(i, cuts[-1] + 1)            # at least one block per band ...
+        i = min(i, nb - (world - k))        # ... and one left for every later band
+        cuts.append(i)
+    cuts.append(nb)
+    return [(cuts[r] * unit, cuts[r + 1] * unit) for r in range(world)]
+
+
 def _ptr(a):
     """Device or host pointer of a numpy array / torch tensor -> (void*, on_device)."""
     if isinstance(a, np.ndarray):

@@ -192,6 +192,10 @@ void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, s
     }
 #define CARRY_CASE(W) if (wps == W) { k_carry<W, 8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); return; }
     CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
+    if (wps > 0) {   // other band heights (work-balanced row bands): 8 segments, looped
+        k_carry_loop<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, wps, e);
+        return;
+    }
     k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e);
 #undef CARRY_CASE
 }

@@ -81,9 +81,9 @@ class CudaBandEngine:
 class ShardedLloyd:
     """The Lloyd loop of gCVT (gcvt.cu:1110-1147, single level) over `world` row bands."""
 
-    def __init__(self, n, rank, world, engine, dist=None):
+    def __init__(self, n, rank, world, engine, dist=None, bands=None):
         self.n, self.rank, self.world = n, rank, world
-        self.row0, self.row1 = row_bands(n, world)[rank]
+        self.row0, self.row1 = (bands or row_bands(n, world))[rank]   # bands: e.g. row_bands_balanced(...)
         self.engine = engine
         self.dist = dist
         self.it = 0

@@ -135,3 +135,28 @@ def test_row_bands_partition():
         assert all((r1 - r0) % 64 == 0 for r0, r1 in b)
     with pytest.raises(ValueError):
         row_bands(256, 8)
+
+
+def test_row_bands_balanced_partition():
+    """Equal-work row bands: a partition (contiguous, multiples of the unit, no empty band), better balanced than
+    equal heights on a density with empty regions, identical for identical inputs, and equal to row_bands when
+    there is nothing to balance."""
+    from surface_remesher_b200 import row_bands, row_bands_balanced
+    import _inputs as I
+    import _oracle as O
+    n = 2048
+    dens = I.density_c3(n)
+    seeds, _, _ = O.seed(dens, I.mask_c3(dens), 6000)
+    ys = np.nonzero(seeds[..., 0] != I.MARK)[0]
+    for w in (2, 4, 8):
+        b = row_bands_balanced(n, w, ys)
+        assert b == row_bands_balanced(n, w, ys.copy())
+        assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+        assert all((r1 - r0) % 64 == 0 and r1 > r0 for r0, r1 in b)
+        load = lambda bands: max(((ys >= a) & (ys < c)).sum() for a, c in bands)
+        assert load(b) <= load(row_bands(n, w))
+    b8 = row_bands_balanced(n, 8, ys)
+    assert max(((ys >= a) & (ys < c)).sum() for a, c in b8) < 0.8 * max(((ys >= a) & (ys < c)).sum() for a, c in row_bands(n, 8))
+    assert row_bands_balanced(1024, 1, ys) == [(0, 1024)]
+    assert row_bands_balanced(1024, 4, np.arange(1024)) == row_bands(1024, 4)      # uniform: equal heights
+    assert all((r1 - r0) % 256 == 0 for r0, r1 in row_bands_balanced(32768, 8, np.random.default_rng(0).integers(8000, 24000, 100000)))

@@ -89,6 +89,24 @@ def test_label_row_band_contexts_agree():
         assert (got != exp[r0:r1]).sum() == 0
 
 
+@pytest.mark.parametrize("n,bands", [(512, [(0, 64), (64, 448), (448, 512)]),          # 2, 12, 2 words: generic column sweep
+                                     (1024, [(0, 256), (256, 768), (768, 1024)]),      # 8 / 16 words: segmented scan
+                                     (2048, [(0, 1280), (1280, 2048)])])               # 40 / 24 words: looped segments
+def test_label_unequal_row_bands(n, bands):
+    """Work-balanced partitions give bands of any height (multiples of 64 rows): every carry-scan variant, with the
+    per-column edge values that summarise the sites above and below the band."""
+    import surface_remesher_b200 as S
+    seeds = I.random_sites(n, 6 * n, 21)
+    seeds[: n // 3] = I.MARK          # an empty region at the top: columns whose nearest site lies in another band
+    exp = O.label_exact(seeds)
+    for (r0, r1) in bands:
+        with S.Context(n, r0, r1) as c:
+            c.set_site_map(np.ascontiguousarray(seeds))
+            c.label()
+            got = c.get_labels()
+        assert (got != exp[r0:r1]).sum() == 0
+
+
 def test_jfa_matches_cpu_jfa_and_error_rate():
     import surface_remesher_b200 as S
     n = 512

@@ -22,18 +22,23 @@ world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dens, mask, vor = bench.make_inputs(n, k, pinned=False)
-r0, r1 = S.row_bands(n, world)[rank]
+bands = S.row_bands_balanced(n, world, np.nonzero(vor[..., 0] != -32768)[0])   # unequal heights: the general case
+r0, r1 = bands[rank]
 eng = CudaBandEngine(n, r0, r1, local)
 eng.set_inputs(dens, mask, vor)
-sl = ShardedLloyd(n, rank, world, eng, dist)
+sl = ShardedLloyd(n, rank, world, eng, dist, bands)
 if mode != "py":
     sl.bind_native_collective(mode)
 sl.run(iters)
 lab = torch.from_numpy(sl.final_labels().copy().view(np.int32).reshape(r1 - r0, n)).cuda()   # short2 -> int32 for NCCL
 sites = np.sort(eng.sites())
 st = eng.state()
-parts = [torch.empty_like(lab) for _ in range(world)]
-dist.all_gather(parts, lab)
+maxr = max(b[1] - b[0] for b in bands)            # bands differ in height: gather padded, cut below
+padded = torch.zeros((maxr, n), dtype=lab.dtype, device="cuda")
+padded[: r1 - r0] = lab
+parts = [torch.empty_like(padded) for _ in range(world)]
+dist.all_gather(parts, padded)
+parts = [parts[q][: bands[q][1] - bands[q][0]] for q in range(world)]
 cs = torch.tensor([int(np.bitwise_xor.reduce(sites.astype(np.int64) * 2654435761 % (1 << 61))), len(sites)], device="cuda")
 allcs = [torch.empty_like(cs) for _ in range(world)]
 dist.all_gather(allcs, cs)
@@ -46,7 +51,7 @@ if rank == 0:
         ref = c.get_labels()
         ref_sites = np.sort(c.get_sites())
         st1 = c.state()
-    out = {"n": n, "world": world, "mode": mode, "iters": iters,
+    out = {"n": n, "world": world, "mode": mode, "iters": iters, "band_rows": [b[1] - b[0] for b in bands],
            "label_mismatches": int((full != ref).any(axis=2).sum()),
            "site_lists_identical_across_ranks": bool(all((a == allcs[0]).all().item() for a in allcs)),
            "sites_equal_single_gpu": bool(np.array_equal(sites, ref_sites)),
