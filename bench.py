@@ -383,8 +383,8 @@ def main():
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl", "py"],
                     help="N>1: p2p = fused all-reduce over peer memory inside the update kernel (default); nccl = NCCL "
                          "all-reduce issued by libsrm; py = torch.distributed all-reduce per step from Python")
-    ap.add_argument("--bands", default="balanced", choices=["balanced", "equal"],
-                    help="N>1: row bands of equal work (sites per block of rows; default) or of equal height")
+    ap.add_argument("--bands", default="equal", choices=["balanced", "equal"],
+                    help="N>1: row bands of equal height (default) or of equal estimated work (row_bands_balanced)")
     ap.add_argument("--_ref_child", action="store_true")
     ap.add_argument("--_inputs", default=None)
     args = ap.parse_args()

@@ -201,12 +201,15 @@ def row_bands(n, world):
     return [(r * h, (r + 1) * h) for r in range(world)]
 
 
-def row_bands_balanced(n, world, site_rows, unit=None, fixed=0.3):
-    """Row bands of roughly equal WORK instead of equal height.  The band kernel's time per row follows the number
-    of sites near the row (band-list and envelope sizes) plus a fixed part (Phase A scans every column), so on
-    densities with empty regions equal-height bands leave the ranks of the dense rows as stragglers (C3 on 8 ranks:
-    1.8x the mean number of sites in the middle bands, 0.1x at the top and bottom).  Weight of a `unit`-row block =
-    sites in the block + `fixed` x the mean; boundaries are multiples of `unit` rows (default: 256 = whole carry
+def row_bands_balanced(n, world, site_rows, unit=None, fixed=2.3):
+    """Row bands of roughly equal WORK instead of equal height.  The band kernel's time per row grows with the number
+    of sites near the row (band-list and envelope sizes) on top of a fixed part (Phase A scans every column, and rows
+    far from any site prune badly), so on densities with empty regions equal-height bands leave the ranks of the dense
+    rows as stragglers (C3 on 8 ranks: 1.8x the mean number of sites in the middle bands, 0.1x at the top and bottom).
+    Weight of a `unit`-row block = sites in the block + `fixed` x the mean.  `fixed` = 2.3 is calibrated on C3 at
+    32768^2 on 8 B200s (0.116 us per sparse row against 0.195 us per dense row); with fixed = 0.3 the sparse bands
+    became the stragglers and every configuration measured slower than equal heights, which is
+    why bench.py defaults to equal heights. boundaries are multiples of `unit` rows (default: 256 = whole carry
     segments for n >= 16384, 64 below).
     Deterministic in its inputs: every rank computes the same partition from the replicated site map.
     site_rows: y coordinates of the sites."""
