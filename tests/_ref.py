@@ -124,3 +124,29 @@ def discretize(points, weight, triangles, scale, n):
     rc = lib().ref_discretize(_p(pts), _p(w), len(w), _p(tri), len(tri), _p(out), float(scale), n)
     assert rc == 0, rc
     return out
+
+
+GDEL_PATH = os.path.join(ROOT, "oracle", "_ref", "libgdel2d_ref.so")
+
+
+def cdt_available():
+    return os.path.exists(GDEL_PATH)
+
+
+def cdt(points, segs, timeout=180):
+    """Constrained Delaunay triangulation by the unmodified reference gDel2D, in a subprocess (tests/_cdt_child.py).
+    Returns (T,3) int32 triangles; raises RuntimeError with the child's stderr if it fails or times out."""
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, "in.npz"), os.path.join(d, "out.npz")
+        np.savez(fi, points=np.ascontiguousarray(points, np.float64), segs=np.ascontiguousarray(segs, np.int32))
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "_cdt_child.py"), fi, fo], capture_output=True,
+                               text=True, timeout=timeout)
+        except subprocess.TimeoutExpired:
+            raise RuntimeError("reference gDel2D timed out")
+        if p.returncode != 0 or not os.path.exists(fo):
+            raise RuntimeError("reference gDel2D failed: " + (p.stderr or p.stdout)[-400:])
+        return np.load(fo)["tri"]

@@ -9,5 +9,5 @@ from surface_remesher_b200 import frontend as FE
 
 V, F = FE.read_off("/root/reference/source/data/nefertiti.off")
 prep = FE.prepare(V, F, 1024)
-np.savez_compressed(os.path.join(HERE, "c1_nefertiti.npz"), F=F, uv=prep["uv"], loop=prep["loop"], weights=prep["weights"])
+np.savez_compressed(os.path.join(HERE, "c1_nefertiti.npz"), V=V, F=F, uv=prep["uv"], loop=prep["loop"], weights=prep["weights"])
 print("saved", len(V), len(F), "border", len(prep["loop"]), "weights", prep["weights"].min(), prep["weights"].max())
