@@ -266,25 +266,26 @@ def run_ours(args):
     }
     if stage is not None and world > 1:
         line["config"]["stages_ms_per_step_rank0"] = {s: v / K for s, v in stage.items()}
-    if stage is not None and world == 1:
+    if stage is not None:
         row_ms = stage["band_fused"] / K
-        # algorithmic bytes of one k_band launch: per 8-row band and column 8 B (bitmap word + up/dn carries)
-        # = N; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
-        alg = 1.0 * N + 52.0 * runs
+        # algorithmic bytes of one k_band launch (rank 0's band at N > 1): per 8-row band and column 8 B (bitmap word +
+        # up/dn carries) = rows * n; per run 8 B written + 16 B fp64 prefix pair + 4 B site id + 24 B accumulator update = 52 B
+        alg = 1.0 * (r1 - r0) * n + 52.0 * runs
         ach = alg / (row_ms / 1e3) / 1e9
         traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of k_band per launch, from the committed ncu capture
         tp = os.path.join(ROOT, "profiles", "r1_k_band_traffic.json")
-        if n == 8192 and k == 100000 and os.path.exists(tp):
+        if n == 8192 and k == 100000 and world == 1 and os.path.exists(tp):
             tj = json.load(open(tp))
             traffic = 0.9 * tj["traffic_normal_step"] + 0.1 * tj["traffic_energy_step"]   # every 10th step computes the energy
-        line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; N B + 52 B/run)",
+        line["roofline"] = {"bound": "hbm", "kernel": "k_band (fused labelling + accumulation; rows*n B + 52 B/run" +
+                                                      ("; rank 0's band)" if world > 1 else ")"),
                             "runs_per_step": runs, "robust_path_rows": ovf,
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                             "peak_source": peak_src, "ms_per_launch": row_ms,
                             "note": "latency / instruction-issue bound, not HBM bound: see DESIGN.md section 4",
                             "stages_ms_per_step": {s: v / K for s, v in stage.items()},
                             "step_bytes_per_px_equiv_GBs": {"8B_per_px": 8.0 * N / (ms / K / 1e3) / 1e9}}
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:   # reported baseline: rank 0 at N = 1 only
         try:
             line["cpu_baseline"] = cpu_baseline(dens, mask, vor, iters=args.cpu_iters)
         except Exception as e:  # pragma: no cover

@@ -960,9 +960,10 @@ out:
 // ------------------------------------------------------------------ locate + lift (recover.h:63-153)
 
 namespace {
-struct DevBufs {   // frees what it allocated when it goes out of scope
+struct DevBufs {   // frees what it allocated (and the locator built on it) when it goes out of scope
     std::vector<void *> p;
-    ~DevBufs() { for (void *q : p) cudaFree(q); }
+    SrmLocator *loc = nullptr;
+    ~DevBufs() { srm_locator_free(loc); for (void *q : p) cudaFree(q); }
     template <typename T> cudaError_t up(T **d, const T *h, size_t count) {
         cudaError_t e = cudaMalloc((void **)d, sizeof(T) * (count ? count : 1));
         if (e != cudaSuccess) return e;
@@ -998,10 +999,10 @@ extern "C" int srm_locate(const double *mesh_xy, int num_vertices, const int *fa
     CK(B.up(&df, (const int *)nullptr, (size_t)num_query));
     CK(B.up(&dw, (const double *)nullptr, 3 * (size_t)num_query));
     CK(srm_locator_build(nullptr, mesh_xy, num_vertices, dp, dt, num_faces, &L));
+    B.loc = L;
     cudaError_t e = srm_locator_query(nullptr, L, dp, dt, dq, nullptr, num_query, df, dw);
     if (e == cudaSuccess && num_query) e = cudaMemcpy(face_out, df, sizeof(int) * num_query, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && num_query && w_out) e = cudaMemcpy(w_out, dw, sizeof(double) * 3 * num_query, cudaMemcpyDeviceToHost);
-    srm_locator_free(L);
     if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_locate: %s", cudaGetErrorString(e));
     return SRM_OK;
 }
@@ -1038,6 +1039,7 @@ extern "C" int srm_recover(const double *mesh_xy, const double *mesh_xyz, int nu
     CK(B.up(&dout, (const double *)nullptr, 3 * (size_t)nfree));
     CK(B.up(&dfc, (const int *)nullptr, (size_t)num_cdt_tri));
     CK(srm_locator_build(nullptr, mesh_xy, num_vertices, dp, dt, num_faces, &L));
+    B.loc = L;
     // sites: locate + barycentric lift (recover.h:94-109); CDT triangles: keep iff the centroid lies in a face (:115-142)
     cudaError_t e = srm_locator_query(nullptr, L, dp, dt, dq, nullptr, nfree, df, dw);
     if (e == cudaSuccess) e = srm_launch_lift(nullptr, dt, d3, df, dw, nfree, dout);
@@ -1046,7 +1048,6 @@ extern "C" int srm_recover(const double *mesh_xy, const double *mesh_xyz, int nu
     if (e == cudaSuccess && nfree) e = cudaMemcpy(vertices_xyz, dout, sizeof(double) * 3 * nfree, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && nfree) e = cudaMemcpy(hf.data(), df, sizeof(int) * nfree, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && num_cdt_tri) e = cudaMemcpy(hfc.data(), dfc, sizeof(int) * num_cdt_tri, cudaMemcpyDeviceToHost);
-    srm_locator_free(L);
     if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_recover: %s", cudaGetErrorString(e));
     // A site that lies in no face: the reference ignores locate's return value and lifts with the PREVIOUS site's
     // face and weights (f_loc is not reset, recover.h:92-96), i.e. repeats the previous vertex.

@@ -79,6 +79,23 @@ def test_argument_errors():
     assert L.srm_discretize(p.ctypes.data, w.ctypes.data, 3, t.ctypes.data, 0, d.ctypes.data, 0.0, 16) == 1  # scale
 
 
+def test_argument_errors_locate_recover():
+    import surface_remesher_b200 as S
+    L = S.lib()
+    pts = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]); p3 = np.zeros((3, 3))
+    tri = np.array([[0, 1, 2]], np.int32); bad = np.array([[0, 1, 5]], np.int32)
+    q = np.array([[0.2, 0.2]]); face = np.zeros(1, np.int32); w = np.zeros(3)
+    assert L.srm_locate(None, 3, tri.ctypes.data, 1, q.ctypes.data, 1, face.ctypes.data, w.ctypes.data) == 1
+    assert L.srm_locate(pts.ctypes.data, 3, bad.ctypes.data, 1, q.ctypes.data, 1, face.ctypes.data, w.ctypes.data) == 1
+    assert b"out of range" in L.srm_last_error()
+    out = np.zeros((1, 3)); keep = np.zeros(1, np.uint8); cdt = np.array([[0, 0, 3]], np.int32); cpv = np.array([9], np.int32)
+    args = lambda c, v, ncp: (pts.ctypes.data, p3.ctypes.data, 3, tri.ctypes.data, 1, q.ctypes.data, 1, v, ncp, c, 1,
+                              out.ctypes.data, keep.ctypes.data, None)
+    assert L.srm_recover(*args(cdt.ctypes.data, None, 0)) == 1            # CDT vertex index out of range
+    assert L.srm_recover(*args(None, cpv.ctypes.data, 1)) == 1            # constraint vertex out of range / null triangles
+    assert L.srm_recover(*args(None, None, 2)) == 1                       # more constraint points than points
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
@@ -89,6 +106,8 @@ def test_no_cpu_fallback():
     v = np.full((256, 256, 2), -32768, np.int16); v[5, 5] = (5, 5)
     with pytest.raises(S.SrmError):
         S.gCVT(v, np.ones((256, 256), np.float32), None, 256, 1, 3)
+    with pytest.raises(S.SrmError, match="no CUDA device"):
+        S.locate(np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0]]), np.array([[0, 1, 2]], np.int32), np.array([[0.2, 0.2]]))
 
 
 def test_product_never_references_the_oracle():
