@@ -209,14 +209,14 @@ def row_bands_balanced(n, world, site_rows, unit=None, fixed=2.3):
     Weight of a `unit`-row block = sites in the block + `fixed` x the mean.  `fixed` = 2.3 is calibrated on C3 at
     32768^2 on 8 B200s (0.116 us per sparse row against 0.195 us per dense row); with fixed = 0.3 the sparse bands
     became the stragglers and every configuration measured slower than equal heights, which is
-    why bench.py defaults to equal heights. boundaries are multiples of `unit` rows (default: 256 = whole carry
-    segments for n >= 16384, 64 below).
+    why bench.py defaults to equal heights. boundaries are multiples of `unit` rows (default 256 = whole carry
+    segments).
     Deterministic in its inputs: every rank computes the same partition from the replicated site map.
     site_rows: y coordinates of the sites."""
     if world == 1:
         return [(0, n)]
     if unit is None:
-        unit = 256 if n >= 16384 else 64
+        unit = 256   # whole carry segments: other heights take the generic column sweep (measured 4 % slower at N = 2)
     if n % unit or n // unit < world:
         return row_bands(n, world)
     nb = n // unit

@@ -149,13 +149,13 @@ def test_row_bands_balanced_partition():
     seeds, _, _ = O.seed(dens, I.mask_c3(dens), 6000)
     ys = np.nonzero(seeds[..., 0] != I.MARK)[0]
     for w in (2, 4, 8):
-        b = row_bands_balanced(n, w, ys, fixed=0.3)
-        assert b == row_bands_balanced(n, w, ys.copy(), fixed=0.3)
+        b = row_bands_balanced(n, w, ys, unit=64, fixed=0.3)
+        assert b == row_bands_balanced(n, w, ys.copy(), unit=64, fixed=0.3)
         assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert all((r1 - r0) % 64 == 0 and r1 > r0 for r0, r1 in b)
         load = lambda bands: max(((ys >= a) & (ys < c)).sum() for a, c in bands)
         assert load(b) <= load(row_bands(n, w))
-    b8 = row_bands_balanced(n, 8, ys, fixed=0.3)
+    b8 = row_bands_balanced(n, 8, ys, unit=64, fixed=0.3)
     assert max(((ys >= a) & (ys < c)).sum() for a, c in b8) < 0.8 * max(((ys >= a) & (ys < c)).sum() for a, c in row_bands(n, 8))
     assert row_bands_balanced(1024, 1, ys) == [(0, 1024)]
     assert row_bands_balanced(1024, 4, np.arange(1024)) == row_bands(1024, 4)      # uniform: equal heights

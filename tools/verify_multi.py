@@ -22,7 +22,7 @@ world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 dens, mask, vor = bench.make_inputs(n, k, pinned=False)
-bands = S.row_bands_balanced(n, world, np.nonzero(vor[..., 0] != -32768)[0])   # unequal heights: the general case
+bands = S.row_bands_balanced(n, world, np.nonzero(vor[..., 0] != -32768)[0], unit=64, fixed=0.3)   # unequal heights: the general case
 r0, r1 = bands[rank]
 eng = CudaBandEngine(n, r0, r1, local)
 eng.set_inputs(dens, mask, vor)
