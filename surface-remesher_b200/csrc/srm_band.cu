@@ -28,6 +28,15 @@
 
 #define BAND_NT 256
 #define BAND_NW 8
+#ifndef BAND_MINCTA
+#define BAND_MINCTA 4      // resident CTAs per SM the register allocation aims at (5 needs <= 48 registers)
+#endif
+#ifndef BAND_C8K
+#define BAND_C8K 1024      // per-warp element buffer (entries) for n <= 8192
+#endif
+#ifndef BAND_CL8K
+#define BAND_CL8K 2816     // band-list capacity (entries) for n <= 8192
+#endif
 
 struct Col8 {          // 8 consecutive columns of one band
     int U[8], D[8];    // nearest site row above / below the band (SRM_MARK if none)
@@ -210,7 +219,7 @@ __device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v,
 #define PROF_CNT(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(v)); } while (0)
 
 template <int RPW, int C, int GS0, int GS1>
-__global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
+__global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
                                                   const short *__restrict__ dn, int n, int row0, int CL,
                                                   int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
@@ -382,8 +391,8 @@ __global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict_
         }
         // output pass: runs -> global run-length row, and (accumulate mode) fp64 prefix differences -> site sums
         int2 *out = rle + (size_t)r * n;
-        const double2 *p2 = P2 + (size_t)r * n;
-        const double *pxx = PXX + (size_t)r * n;
+        const double2 *p2 = P2 + srm_pfx_row(r, n);   // tiled layout: element x at [x * SRM_PFX_TILE]
+        const double *pxx = PXX + srm_pfx_row(r, n);
         int carryB = -1;
         double2 carryP = make_double2(0, 0);
         double carryXX = 0;
@@ -408,8 +417,8 @@ __global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict_
                 int id[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {  // all loads of both chunks first
-                    pb[q] = (st[q].owned && !(dbg & 8)) ? p2[st[q].B] : make_double2(1, 1);
-                    xb[q] = (st[q].owned && want_energy) ? pxx[st[q].B] : 0;
+                    pb[q] = (st[q].owned && !(dbg & 8)) ? p2[(size_t)st[q].B * SRM_PFX_TILE] : make_double2(1, 1);
+                    xb[q] = (st[q].owned && want_energy) ? pxx[(size_t)st[q].B * SRM_PFX_TILE] : 0;
                     id[q] = st[q].owned ? ((dbg & 4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
                 }
 #pragma unroll
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(BAND_NT, 4) k_band(const uint32_t *__restrict_
 
 // Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62.  Rows of an n-wide grid with the
 // BASELINE site densities have ~n/26 runs (316 at 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
-static int band_bufcap(int n) { return n <= 8192 ? 1024 : n <= 16384 ? 1280 : 1792; }
+static int band_bufcap(int n) { return n <= 8192 ? BAND_C8K : n <= 16384 ? 1280 : 1792; }
 
 static int band_cap(int n) {
     // Band-list capacity.  Measured on C3-like inputs with the 3-block pruning: band list mean 0.11 n, max
@@ -467,7 +476,7 @@ static int band_cap(int n) {
     //   n <= 32768: 6144 entries -> 108 KB -> 2 CTAs/SM
     // A band or row that exceeds them goes to the robust path (k_row), which has worst-case capacity.
     int cl = (3 * n) / 8;
-    const int cap = n <= 8192 ? 2816 : n <= 16384 ? 3584 : 6144;
+    const int cap = n <= 8192 ? BAND_CL8K : n <= 16384 ? 3584 : 6144;
     if (cl > cap) cl = cap;
     if (cl < 512) cl = 512;
     return cl;
@@ -488,8 +497,8 @@ cudaError_t srm_band_setup(int n) {
     (void)n;
     const int s8 = (int)band_smem(8192, band_cap(8192)), s16 = (int)band_smem(16384, band_cap(16384)),
               s32 = (int)band_smem(32768, band_cap(32768));
-    cudaError_t e = band_setup_one<1, 1024>(s8);
-    if (e == cudaSuccess) e = band_setup_one<2, 1024>(s8);
+    cudaError_t e = band_setup_one<1, BAND_C8K>(s8);
+    if (e == cudaSuccess) e = band_setup_one<2, BAND_C8K>(s8);
     if (e == cudaSuccess) e = band_setup_one<1, 1280>(s16);
     if (e == cudaSuccess) e = band_setup_one<2, 1280>(s16);
     if (e == cudaSuccess) e = band_setup_one<1, 1792>(s32);
@@ -526,7 +535,7 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
     const size_t smem = band_smem(g.n, CL);
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
 #define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop, dbg
-    if (C == 1024) { if (rpw == 1) band_launch_one<1, 1024>(BAND_ARGS); else band_launch_one<2, 1024>(BAND_ARGS); }
+    if (C == BAND_C8K) { if (rpw == 1) band_launch_one<1, BAND_C8K>(BAND_ARGS); else band_launch_one<2, BAND_C8K>(BAND_ARGS); }
     else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
     else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }
 #undef BAND_ARGS

@@ -106,8 +106,8 @@ __device__ __forceinline__ double acc_row(const int2 *rr, int cnt, const double2
         int2 v = act ? rr[e] : make_int2(0, 0);
         int b = n - 1;
         if (act && e + 1 < cnt) b = rr[e + 1].y - 1;
-        double2 pb = act ? p2[b] : make_double2(0, 0);
-        double xb = (act && want_energy) ? pxx[b] : 0;
+        double2 pb = act ? p2[(size_t)b * SRM_PFX_TILE] : make_double2(0, 0);   // p2 / pxx: row bases (srm_pfx_row)
+        double xb = (act && want_energy) ? pxx[(size_t)b * SRM_PFX_TILE] : 0;
         double2 pa;
         pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1);
         pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);

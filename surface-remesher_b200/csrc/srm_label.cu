@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
         }
         __syncthreads();
         if (accumulate && w == 0) {
-            double e_loc = acc_row(rle + (size_t)r * n, wtot[0], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, Y, acc,
+            double e_loc = acc_row(rle + (size_t)r * n, wtot[0], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, Y, acc,
                                    Kcap, want_energy, lane);
             if (want_energy) {
                 e_loc = warp_sum(e_loc);

@@ -51,11 +51,11 @@ __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ den
             tw += sw[0][k]; tx += sw[1][k]; txx += sw[2][k];
         }
         if (in) {
-            size_t o = (size_t)r * n + x;
+            const size_t o = srm_pfx_row(r, n) + (size_t)x * SRM_PFX_TILE;   // tiled layout, srm_common.cuh
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                P2[o + k] = make_double2(ew + W[k], ex + X[k]);
-                PXX[o + k] = exx + XX[k];
+                P2[o + (size_t)k * SRM_PFX_TILE] = make_double2(ew + W[k], ex + X[k]);
+                PXX[o + (size_t)k * SRM_PFX_TILE] = exx + XX[k];
             }
         }
         cW += tw; cX += tx; cXX += txx;
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
     double e_loc = 0;
     for (int q = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5); q < total; q += nwarps) {
         const int r = rows ? rows[q] : q;
-        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + (size_t)r * n, PXX + (size_t)r * n, idmap, n, row0 + r, acc,
+        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, row0 + r, acc,
                          Kcap, want_energy, lane);
     }
     if (want_energy) {
