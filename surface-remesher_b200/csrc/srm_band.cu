@@ -141,6 +141,29 @@ __device__ __forceinline__ int breakpoint(int num, int den, int n) {
     return min(q, n - 1);
 }
 
+#ifndef BAND_NCH
+#define BAND_NCH 2     // 31-element chunks in flight per iteration of the round loop over the element buffer
+#endif
+#ifndef BAND_LUT
+#define BAND_LUT 0     // > 0: neighbours less than BAND_LUT columns apart take their quotient estimate from a shared-memory
+#endif                 // table of reciprocals (one LDS + IMAD.HI) instead of I2F, I2F, MUFU.RCP, F2I (four XU-pipe operations)
+
+// Same result as breakpoint(num, 2 * gap, n).  lut[g] = floor(2^32 / (2g)) + 1, so umulhi(num, lut[g]) is the true
+// quotient or one more for 0 <= num < 2^31 (excess num * eps / 2^32 < 1/2); the +-1 fix-up below makes it exact.
+__device__ __forceinline__ int breakpoint_gap(int num, int gap, int n, const unsigned *__restrict__ lut) {
+#if BAND_LUT > 0
+    if ((unsigned)gap < (unsigned)BAND_LUT) {
+        const int den = 2 * gap;
+        int q = (int)__umulhi((unsigned)max(num, 0), lut[gap]);
+        q = min(q, n);
+        const int r = num - q * den;
+        q += (int)(r >= den) - (int)(r < 0);
+        return min(q, n - 1);
+    }
+#endif
+    return breakpoint(num, 2 * gap, n);
+}
+
 // Candidate of band-list entry i for row Y = Y0 + k: packed x | c << 16 and H = x^2 + (c - Y)^2.
 __device__ __forceinline__ void load_cand(const uint2 *__restrict__ L, int i, int Y0, int k, int Y, unsigned &v, int &x,
                                           int &H) {
@@ -162,12 +185,12 @@ struct RoundStep {
     bool owned, keep;
 };
 __device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
-                                                int &carryB) {
+                                                int &carryB, const unsigned *__restrict__ lut) {
     RoundStep r;
     const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
     const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
     r.owned = valid && lane < 31;
-    r.B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
+    r.B = validn ? breakpoint_gap(Hn - H, xn - x, n, lut) : n - 1;
     r.Bc = __shfl_up_sync(0xffffffffu, r.B, 1);
     if (lane == 0) r.Bc = carryB;
     carryB = __shfl_sync(0xffffffffu, r.B, 30);
@@ -182,11 +205,11 @@ __device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigne
 // the breakpoint of (last owned element, lookahead element) from the Jacobi step: a valid bound either way.
 template <int MAX_INNER>
 __device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
-                                            int &carryB) {
+                                            int &carryB, const unsigned *__restrict__ lut) {
     const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
     const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
     const bool owned = valid && lane < 31;
-    int B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
+    int B = validn ? breakpoint_gap(Hn - H, xn - x, n, lut) : n - 1;
     int Bc = __shfl_up_sync(0xffffffffu, B, 1);
     if (lane == 0) Bc = carryB;
     carryB = __shfl_sync(0xffffffffu, B, 30);
@@ -204,7 +227,7 @@ __device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v,
         const int pl = left ? 31 - __clz(left) : 0;         // nearest kept lane to the left
         const unsigned vr = __shfl_sync(0xffffffffu, v, nl);
         const int xr = (int)(vr & 0xffffu), gr = (int)(vr >> 16) - Y, Hr = xr * xr + gr * gr;
-        const int Bn = right ? breakpoint(Hr - H, 2 * (xr - x), n) : n - 1;  // against my nearest kept right neighbour
+        const int Bn = right ? breakpoint_gap(Hr - H, xr - x, n, lut) : n - 1;  // against my nearest kept right neighbour
         const int Bl = __shfl_sync(0xffffffffu, Bn, pl);  // B(nearest kept left neighbour, me): just computed against me
         B = min(B, Bn);                 // both are bounds by real candidates to my right
         if (left) Bc = max(Bc, Bl);     // likewise on the left (without a kept left lane the Jacobi bound stays)
@@ -235,6 +258,14 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     uint2 *L = reinterpret_cast<uint2 *>(smem_raw);                       // band list: {x | inband << 16, U | D << 16}
     unsigned char *masks = reinterpret_cast<unsigned char *>(L + CL);      // live mask per 8-column block
     unsigned *buf0 = reinterpret_cast<unsigned *>(masks + ((n / 8 + 15) & ~15));  // per-warp element buffers
+    const unsigned *lut = nullptr;
+#if BAND_LUT > 0
+    {   // reciprocal table behind the element buffers; entry 0 is never used (neighbours are at least one column apart)
+        unsigned *lw = buf0 + (size_t)BAND_NW * C;
+        for (int g = threadIdx.x; g < BAND_LUT; g += BAND_NT) lw[g] = g ? (unsigned)(0x100000000ull / (unsigned long long)(2 * g)) + 1u : 0u;
+        lut = lw;   // published by the __syncthreads() that ends Phase A
+    }
+#endif
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     const int rb = blockIdx.x * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
@@ -345,8 +376,8 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 int x0 = 0, H0 = 0, x1 = 0, H1 = 0;
                 load_cand(L, min(ea, mb - 1), Y0, k, Y, v0, x0, H0);  // clamped index: no branch, result unused if !va
                 load_cand(L, min(eb, mb - 1), Y0, k, Y, v1, x1, H1);
-                const bool ka = chunk_round<GS0>(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0);
-                const bool kb = chunk_round<GS0>(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0);
+                const bool ka = chunk_round<GS0>(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0, lut);
+                const bool kb = chunk_round<GS0>(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0, lut);
                 const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
                 if (ka) buf[m + __popc(ba & lt)] = v0;
                 m += __popc(ba);
@@ -359,20 +390,32 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             // rounds over buf until nothing is dropped
             for (;;) {
                 int wp = 0, carryB = -1;
-                for (int base = 0; base < m; base += 62) {
-                    const int ea = base + lane, eb = base + 31 + lane;
-                    const bool va = ea < m, vb = eb < m;
-                    const unsigned v0 = va ? buf[ea] : 0u, v1 = vb ? buf[eb] : 0u;
-                    const int x0 = (int)(v0 & 0xffffu), g0 = (int)(v0 >> 16) - Y, H0 = x0 * x0 + g0 * g0;
-                    const int x1 = (int)(v1 & 0xffffu), g1 = (int)(v1 >> 16) - Y, H1 = x1 * x1 + g1 * g1;
-                    const bool ka = chunk_round<GS1>(va, ea + 1 < m, v0, x0, H0, Y, lane, n, carryB);
-                    const bool kb = chunk_round<GS1>(vb, eb + 1 < m, v1, x1, H1, Y, lane, n, carryB);
-                    const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
+                for (int base = 0; base < m; base += 31 * BAND_NCH) {
+                    // BAND_NCH independent 31-element chunks per iteration (only the carry shuffle links them)
+                    unsigned vv[BAND_NCH], bal[BAND_NCH];
+                    bool kk[BAND_NCH];
+                    int xs[BAND_NCH], Hs[BAND_NCH];
+#pragma unroll
+                    for (int q = 0; q < BAND_NCH; ++q) {
+                        const int e = base + 31 * q + lane;
+                        vv[q] = (e < m) ? buf[e] : 0u;
+                        xs[q] = (int)(vv[q] & 0xffffu);
+                        const int g = (int)(vv[q] >> 16) - Y;
+                        Hs[q] = xs[q] * xs[q] + g * g;
+                    }
+#pragma unroll
+                    for (int q = 0; q < BAND_NCH; ++q) {
+                        const int e = base + 31 * q + lane;
+                        kk[q] = chunk_round<GS1>(e < m, e + 1 < m, vv[q], xs[q], Hs[q], Y, lane, n, carryB, lut);
+                    }
+#pragma unroll
+                    for (int q = 0; q < BAND_NCH; ++q) bal[q] = __ballot_sync(0xffffffffu, kk[q]);
                     __syncwarp();
-                    if (ka) buf[wp + __popc(ba & lt)] = v0;
-                    wp += __popc(ba);
-                    if (kb) buf[wp + __popc(bb & lt)] = v1;
-                    wp += __popc(bb);
+#pragma unroll
+                    for (int q = 0; q < BAND_NCH; ++q) {
+                        if (kk[q]) buf[wp + __popc(bal[q] & lt)] = vv[q];
+                        wp += __popc(bal[q]);
+                    }
                 }
                 __syncwarp();
                 const bool removed = wp != m;
@@ -408,7 +451,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 xx[q] = (int)(vv[q] & 0xffffu); cc[q] = (int)(vv[q] >> 16);
                 const int g = cc[q] - Y;
                 HH[q] = xx[q] * xx[q] + g * g;
-                st[q] = round_step(valid, ee[q] + 1 < m, vv[q], xx[q], HH[q], Y, lane, n, carryB);
+                st[q] = round_step(valid, ee[q] + 1 < m, vv[q], xx[q], HH[q], Y, lane, n, carryB, lut);
                 if (st[q].owned) out[ee[q]] = make_int2((int)vv[q], st[q].Bc + 1);
             }
             if (accumulate) {
@@ -483,7 +526,7 @@ static int band_cap(int n) {
 }
 
 static size_t band_smem(int n, int CL) {
-    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4;
+    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4 + (size_t)BAND_LUT * 4;
 }
 
 template <int RPW, int C>

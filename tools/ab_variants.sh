@@ -4,7 +4,7 @@ OUT=gpurun_out; mkdir -p $OUT
 for v in base "$@"; do
   if [ $v = base ]; then unset SRM_LIB; else export SRM_LIB=$PWD/build/variants/libsrm_$v.so; fi
   python -m pytest tests/test_gpu_lloyd.py -m gpu -x -q -k "whole_gcvt or baseline_sizes or full" 2>&1 | tail -1
-  python bench.py --no-cpu --steps 500 --warmup 30 > $OUT/ab_$v.json 2> $OUT/ab_$v.err
+  python bench.py --no-cpu --steps 300 --warmup 20 --e2e-iters 50 > $OUT/ab_$v.json 2> $OUT/ab_$v.err
   python - <<PY
 import json
 d=json.loads(open("$OUT/ab_$v.json").read().strip().splitlines()[-1])
