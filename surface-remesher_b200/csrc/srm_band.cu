@@ -141,6 +141,9 @@ __device__ __forceinline__ int breakpoint(int num, int den, int n) {
     return min(q, n - 1);
 }
 
+#ifndef BAND_PERSIST
+#define BAND_PERSIST 0 // 1: persistent CTAs that take bands from a ticket (grid = resident CTAs) instead of one CTA per band
+#endif
 #ifndef BAND_NCH
 #define BAND_NCH 2     // 31-element chunks in flight per iteration of the round loop over the element buffer
 #endif
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                   const int *__restrict__ idmap, double *__restrict__ acc, int Kcap,
                                                   SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
-                                                  int dbg) {
+                                                  int dbg, int nbands) {
     constexpr int R = BAND_NW * RPW;
     static_assert(R <= 16, "in-band bits are packed in 16 bits");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -268,7 +271,25 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
 #endif
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int rb = blockIdx.x * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
+    double e_loc = 0;
+    __shared__ int stage_ovf;
+#if BAND_PERSIST
+    // Persistent form: the grid holds as many CTAs as are resident at once and every CTA takes bands from a ticket
+    // until none is left, so an SM keeps its full complement of CTAs until the very end (no partial second wave).
+    __shared__ int s_band;
+    for (;;) {
+        __syncthreads();   // every warp is done with the previous band's shared memory
+        if (t == 0) { s_band = atomicAdd(&ctl->band_ticket, 1); stage_ovf = 0; }
+        __syncthreads();
+        const int bi = s_band;
+        if (bi >= nbands) break;
+#else
+    {
+        const int bi = blockIdx.x;
+        (void)nbands;
+        if (t == 0) stage_ovf = 0;
+#endif
+    const int rb = bi * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
     const size_t wrow = (size_t)j * n;
     const int nb = n >> 3;
     const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
@@ -277,8 +298,6 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     // ---- Phase A, pass 1: live mask of every 8-column block (30 owned blocks per step + one halo block each side).
     // Live columns are staged, in order, in the warp's own (still unused) element buffer so that the list can be
     // assembled by a plain copy once the per-warp offsets are known.
-    __shared__ int stage_ovf;
-    if (t == 0) stage_ovf = 0;
     uint2 *stage = reinterpret_cast<uint2 *>(buf0 + (size_t)w * C);
     constexpr int STAGE_CAP = C / 2;
     int mycount = 0;
@@ -325,7 +344,11 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     if ((dbg & 1) && t == 0) { atomicMax(&ctl->dbg[0], mb); atomicAdd(&ctl->dbg[1], mb); atomicAdd(&ctl->dbg[2], 1); }
     if (mb > CL) {  // band list does not fit: every row of the band goes to the robust path
         if (t < R) ovf_rows[atomicAdd(&ctl->ovf, 1)] = rb + t;
+#if BAND_PERSIST
+        continue;
+#else
         return;
+#endif
     }
     if (!stage_ovf) {
         // ---- assemble the band list: copy the staged entries to their place
@@ -362,7 +385,6 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     // latency bound: ncu short/long scoreboard stalls, profiles/r1_ncu_full_summary.md).
     unsigned *buf = buf0 + (size_t)w * C;
     const unsigned lt = (1u << lane) - 1u;
-    double e_loc = 0;
     for (int rr = 0; rr < RPW; ++rr) {
         const int k = w * RPW + rr, r = rb + k, Y = Y0 + k;
         int m = 0, pos = 0, carry0 = -1;
@@ -493,6 +515,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         PROF_ADD(5);   // output + accumulate
         PROF_CNT(14, m);
     }
+    }   // band (loop in the persistent form)
     if (accumulate && want_energy) {
         e_loc = warp_sum(e_loc);
         if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
@@ -565,9 +588,21 @@ static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, 
                             int CL, int2 *rle, int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX,
                             const int *idmap, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
                             int respect_stop, int dbg) {
-    k_band<RPW, C, BAND_GS0, BAND_GS1><<<g.nrows() / (BAND_NW * RPW), BAND_NT, smem, st>>>(
+    const int nbands = g.nrows() / (BAND_NW * RPW);
+    int grid = nbands;
+#if BAND_PERSIST
+    {
+        static int per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}}, sms = 0;   // resident CTAs per SM of this instantiation
+        const int ci = C == BAND_C8K ? 0 : C == 1280 ? 1 : 2;
+        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+        if (!per_sm[RPW - 1][ci])
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[RPW - 1][ci], k_band<RPW, C, BAND_GS0, BAND_GS1>, BAND_NT, smem);
+        grid = min(nbands, max(1, per_sm[RPW - 1][ci]) * max(1, sms));
+    }
+#endif
+    k_band<RPW, C, BAND_GS0, BAND_GS1><<<grid, BAND_NT, smem, st>>>(
         bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
-        respect_stop, dbg);
+        respect_stop, dbg, nbands);
 }
 
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,

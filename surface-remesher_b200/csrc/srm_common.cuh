@@ -21,6 +21,7 @@ struct SrmCtl {
     float lastE;    // lastEnergy
     float E;        // Energy (float like the reference)
     int ovf;        // rows handed to the robust path by the band kernel (this labelling)
+    int band_ticket; // next band of the persistent band kernel (reset with ovf by k_bits)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
     float escale;    // multires: energy factor 4^level (gcvt.cu:1082); 1 on the finest level

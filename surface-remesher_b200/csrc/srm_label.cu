@@ -28,7 +28,7 @@
 __global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32_t *bits, int *idmap, int *claim,
                        int respect_stop, int row0, int row1, int *edge) {
     if (respect_stop && ctl->stop) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ovf = 0;  // rows the band kernel hands to the robust path
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->ovf = 0; ctl->band_ticket = 0; }  // robust-path row list, band ticket
     int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
     int p = sites[id];
