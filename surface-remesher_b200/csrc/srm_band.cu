@@ -240,6 +240,39 @@ __device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v,
     return keep;
 }
 
+#ifndef BAND_SITETAB
+#define BAND_SITETAB 0   // > 0 (slots, e.g. 768): per-band shared-memory table that sums a site's runs over the band's rows,
+#endif                   // so that the site-id lookup and the three global fp64 REDs happen once per site per band instead
+                         // of once per run (~6x fewer).  PREPARED IN ROUND 1 WITHOUT GPU TIME LEFT: compiles, never run.
+
+#if BAND_SITETAB > 0
+#define SITETAB_EMPTY 0xffffffffu   // no packed site has the top bit set (row < 32768)
+struct SiteTab {
+    unsigned *key;     // packed site (x | c << 16) or SITETAB_EMPTY
+    double *sum;       // 3 doubles per slot: W, X, Y*W
+};
+__device__ __forceinline__ unsigned sitetab_slot(unsigned v) {
+    return (unsigned)(((unsigned long long)(v * 2654435761u) * (unsigned)BAND_SITETAB) >> 32);   // multiplicative hash -> [0, slots)
+}
+// Adds a run's sums to its site's slot; false if no slot was found within a few probes (the caller then updates the
+// global accumulators directly, as the table-less kernel does).
+__device__ __forceinline__ bool sitetab_add(const SiteTab &T, unsigned v, double W, double X, double YW) {
+    unsigned h = sitetab_slot(v);
+#pragma unroll 1
+    for (int probe = 0; probe < 8; ++probe) {
+        const unsigned k = atomicCAS(&T.key[h], SITETAB_EMPTY, v);
+        if (k == SITETAB_EMPTY || k == v) {
+            atomicAdd(&T.sum[3 * h], W);
+            atomicAdd(&T.sum[3 * h + 1], X);
+            atomicAdd(&T.sum[3 * h + 2], YW);
+            return true;
+        }
+        h = (h + 1 == (unsigned)BAND_SITETAB) ? 0u : h + 1;
+    }
+    return false;
+}
+#endif
+
 #define PROF_T0() long long t0__ = (dbg & 1) ? clock64() : 0
 #define PROF_ADD(slot) do { if (dbg & 1) { long long t1__ = clock64(); if (lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
 #define PROF_CNT(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(v)); } while (0)
@@ -271,6 +304,14 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
 #endif
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+#if BAND_SITETAB > 0
+    SiteTab tab;
+    {   // behind the element buffers and the reciprocal table; 8-byte aligned (all sizes before it are multiples of 16)
+        unsigned char *tb = reinterpret_cast<unsigned char *>(buf0 + (size_t)BAND_NW * C + BAND_LUT);
+        tab.sum = reinterpret_cast<double *>(tb);
+        tab.key = reinterpret_cast<unsigned *>(tb + (size_t)BAND_SITETAB * 24);
+    }
+#endif
     double e_loc = 0;
     __shared__ int stage_ovf;
 #if BAND_PERSIST
@@ -290,6 +331,10 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         if (t == 0) stage_ovf = 0;
 #endif
     const int rb = bi * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
+#if BAND_SITETAB > 0
+    if (accumulate)   // cleared here, first used after the two barriers of Phase A
+        for (int q = t; q < BAND_SITETAB; q += BAND_NT) { tab.key[q] = SITETAB_EMPTY; tab.sum[3 * q] = 0; tab.sum[3 * q + 1] = 0; tab.sum[3 * q + 2] = 0; }
+#endif
     const size_t wrow = (size_t)j * n;
     const int nb = n >> 3;
     const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
@@ -484,7 +529,11 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 for (int q = 0; q < 2; ++q) {  // all loads of both chunks first
                     pb[q] = (st[q].owned && !(dbg & 8)) ? p2[(size_t)st[q].B * SRM_PFX_TILE] : make_double2(1, 1);
                     xb[q] = (st[q].owned && want_energy) ? pxx[(size_t)st[q].B * SRM_PFX_TILE] : 0;
+#if BAND_SITETAB > 0
+                    id[q] = -1;   // looked up only by the runs that find no table slot
+#else
                     id[q] = st[q].owned ? ((dbg & 4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
+#endif
                 }
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -498,8 +547,14 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                     carryXX = __shfl_sync(0xffffffffu, xb[q], 30);
                     if (st[q].owned) {
                         const double W = pb[q].x - pa.x, X = pb[q].y - pa.y;
+#if BAND_SITETAB > 0
+                        if (!sitetab_add(tab, vv[q], W, X, (double)Y * W)) id[q] = idmap[(size_t)cc[q] * n + xx[q]];
+                        double *a = acc + 4 * (size_t)max(id[q], 0);
+                        if (id[q] >= 0) {
+#else
                         double *a = acc + 4 * (size_t)id[q];
                         if (!(dbg & 2)) {
+#endif
                             atomicAdd(a, W);
                             atomicAdd(a + 1, X);
                             atomicAdd(a + 2, (double)Y * W);
@@ -515,6 +570,21 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         PROF_ADD(5);   // output + accumulate
         PROF_CNT(14, m);
     }
+#if BAND_SITETAB > 0
+    if (accumulate) {   // every warp's rows are in the table: one id lookup and one set of global REDs per site of the band
+        __syncthreads();
+        for (int q = t; q < BAND_SITETAB; q += BAND_NT) {
+            const unsigned v = tab.key[q];
+            if (v == SITETAB_EMPTY) continue;
+            const int id = idmap[(size_t)(v >> 16) * n + (v & 0xffffu)];
+            double *a = acc + 4 * (size_t)id;
+            atomicAdd(a, tab.sum[3 * q]);
+            atomicAdd(a + 1, tab.sum[3 * q + 1]);
+            atomicAdd(a + 2, tab.sum[3 * q + 2]);
+            reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id] = 1;
+        }
+    }
+#endif
     }   // band (loop in the persistent form)
     if (accumulate && want_energy) {
         e_loc = warp_sum(e_loc);
@@ -549,7 +619,8 @@ static int band_cap(int n) {
 }
 
 static size_t band_smem(int n, int CL) {
-    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4 + (size_t)BAND_LUT * 4;
+    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4 + (size_t)BAND_LUT * 4 +
+           (size_t)BAND_SITETAB * 28;   // site table: 3 doubles + key per slot
 }
 
 template <int RPW, int C>
