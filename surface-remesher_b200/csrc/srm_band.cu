@@ -22,6 +22,19 @@
 //     run to its site's accumulators (centroid + energy).
 // A band whose list exceeds CL entries, or a row whose envelope exceeds the buffer, is handed to the
 // robust path (k_row in srm_label.cu).
+//
+// Compile-time switches (defaults = the measured best; every alternative was A/B-measured on a B200 unless noted,
+// profiles/r1_kernel_log.md):
+//   BAND_REACH    3   neighbouring 8-column blocks per side used by the band-level pruning (1: band list 1.7x longer)
+//   BAND_GS0/GS1  0   in-chunk Gauss-Seidel sweeps in round 0 / later rounds (fewer passes, same time)
+//   BAND_NCH      2   chunks in flight in the round loop (3, 4: no effect)
+//   BAND_LUT      0   reciprocal table instead of the float division in the breakpoint (512: exact, no effect)
+//   BAND_MINCTA   4   resident CTAs per SM the register allocation aims at; BAND_C8K / BAND_CL8K = buffer and band-list
+//                     capacities for n <= 8192 (5 or 6 CTAs per SM with smaller capacities: no gain / slower)
+//   BAND_PERSIST  0   persistent CTAs taking bands from a ticket (same results, 3 % slower)
+//   BAND_SITETAB  0   per-band shared-memory site table for the accumulation (written, NOT yet run on a GPU)
+//   SRM_PFX_TILE  1   (srm_common.cuh) rows interleaved in the fp64 prefix arrays (8: kernel -1 %, k_prefix slower)
+// Variants are built into build/variants/ and compared in one process with tools/ab_inproc.py.
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
 #include <stdlib.h>
