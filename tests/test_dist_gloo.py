@@ -81,7 +81,7 @@ class OracleBandEngine:
         return self.lab[self.row0:self.row1]
 
 
-def _worker(rank, world, port, n, k, iters, q):
+def _worker(rank, world, port, n, k, iters, q, bands=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -91,10 +91,10 @@ def _worker(rank, world, port, n, k, iters, q):
     dens = I.density_c3(n)
     mask = I.mask_c3(dens)
     seeds, _, _ = O.seed(dens, mask, k)
-    r0, r1 = row_bands(n, world)[rank]
+    r0, r1 = (bands or row_bands(n, world))[rank]
     eng = OracleBandEngine(n, r0, r1)
     eng.set_inputs(dens, mask, seeds)
-    sl = ShardedLloyd(n, rank, world, eng, dist)
+    sl = ShardedLloyd(n, rank, world, eng, dist, bands)
     sl.run(iters)
     lab = sl.final_labels()
     q.put((rank, r0, r1, lab, sorted(eng.sites)))
@@ -106,12 +106,17 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def test_two_band_lloyd_equals_single_process():
-    n, k, iters, world = 128, 60, 12, 2
+@pytest.mark.parametrize("bands", [None, [(0, 64), (64, 128)], [(0, 64), (64, 128), (128, 256)]],
+                         ids=["equal-2", "explicit-2", "unequal-3"])
+def test_two_band_lloyd_equals_single_process(bands):
+    """world_size 2 (equal bands, and the same partition passed explicitly) and world_size 3 with bands of unequal
+    height (64 / 64 / 128 rows), as row_bands_balanced produces them."""
+    world = len(bands) if bands else 2
+    n, k, iters = (256, 80, 6) if world == 3 else (128, 60, 12)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, k, iters, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, k, iters, q, bands)) for r in range(world)]
     for p in procs: p.start()
     res = [q.get(timeout=300) for _ in range(world)]
     for p in procs: p.join(timeout=60)
@@ -121,7 +126,7 @@ def test_two_band_lloyd_equals_single_process():
     exp, it, _, _ = O.gcvt(seeds, dens, mask, iters, stop_rule=0)
     assert it == iters
     res.sort()
-    assert res[0][4] == res[1][4], "replicated site lists diverged between ranks"
+    assert all(r[4] == res[0][4] for r in res), "replicated site lists diverged between ranks"
     full = np.concatenate([r[3] for r in res], axis=0)
     assert (full != exp).sum() == 0
 
