@@ -24,6 +24,24 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, nm), nm
 
 
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/srm.h must be usable from C (the boundary is a C ABI): compile and link the C example against libsrm.so;
+    without a GPU it must fail loudly with SRM_ERR_CUDA (exit code 3), not fall back to anything."""
+    import subprocess
+    import surface_remesher_b200 as S
+    exe = str(tmp_path / "gcvt_c_abi")
+    libdir = os.path.dirname(S.lib_path())
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "gcvt_c_abi.c"), "-o", exe, "-L", libdir, "-lsrm",
+                           f"-Wl,-rpath,{libdir}"])
+    import torch
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert p.returncode == 0 and "iterations" in p.stdout, p.stderr
+    else:
+        assert p.returncode == 3 and "no CUDA device" in p.stderr, (p.returncode, p.stderr)
+
+
 def test_dropin_library_exports_reference_signatures():
     so = os.path.join(ROOT, "surface-remesher_b200", "libsrm_dropin.so")
     L = C.CDLL(so)
