@@ -42,6 +42,24 @@ def test_header_is_plain_c_and_example_links(tmp_path):
         assert p.returncode == 3 and "no CUDA device" in p.stderr, (p.returncode, p.stderr)
 
 
+def test_dropin_caller_links_and_fails_like_gpuErrchk(tmp_path):
+    """A C++ caller that only declares gCVT / discretization_d (as gcvt.h:29 and discretization.h:66 do) links against
+    libsrm_dropin.so; without a GPU the shim reproduces the reference's error behaviour (gcvt.cu:41-47): a
+    `GPUassert: ...` line on stderr and exit(code)."""
+    import subprocess
+    import surface_remesher_b200 as S
+    exe = str(tmp_path / "dropin_caller")
+    libdir = os.path.dirname(S.lib_path())
+    subprocess.check_call(["/usr/bin/g++", "-std=c++14", "-Wall", os.path.join(ROOT, "examples", "dropin_caller.cpp"), "-o", exe,
+                           "-L", libdir, "-lsrm_dropin", "-lsrm", f"-Wl,-rpath,{libdir}"])
+    import torch
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    if torch.cuda.is_available():
+        assert p.returncode == 0 and "gcvtIterations" in p.stdout, p.stderr
+    else:
+        assert p.returncode == 2 and p.stderr.startswith("GPUassert: "), (p.returncode, p.stderr)
+
+
 def test_dropin_library_exports_reference_signatures():
     so = os.path.join(ROOT, "surface-remesher_b200", "libsrm_dropin.so")
     L = C.CDLL(so)
@@ -135,3 +153,10 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dp, f)).read()
                 assert "liboracle" not in txt and "_oracle" not in txt and "orc_" not in txt, f
+
+
+@pytest.mark.gpu
+def test_examples_run_on_the_gpu(tmp_path):
+    """The same two programs on a GPU box: the C-ABI example and the drop-in caller complete a Lloyd run."""
+    test_header_is_plain_c_and_example_links(tmp_path)
+    test_dropin_caller_links_and_fails_like_gpuErrchk(tmp_path)
