@@ -156,6 +156,11 @@ int srm_run(srm_ctx *ctx, int max_iter, int stop_rule, srm_stats *stats);
 int srm_get_state(srm_ctx *ctx, srm_stats *stats);
 /* Measurement helper: runs produced by the last labelling and rows that took the robust path. */
 int srm_debug_counts(srm_ctx *ctx, long long *total_runs, int *overflow_rows);
+/* Kernels launched by this library since it was loaded (process-wide; memsets and copies are not counted). */
+long long srm_launch_count(void);
+/* Statistics counter of the band kernel, collected while the option "dbg_stats" is 1: which = 0 max / 1 sum of the
+ * band-list length, 2 bands, 6 warps that took the staging-overflow fallback of Phase A. */
+int srm_debug_get(srm_ctx *ctx, int which, long long *value);
 
 /* Dense labels of this band (rows row0..row1): expands the run-length labels of the last srm_label.
  * out: (row1-row0)*n short2. */

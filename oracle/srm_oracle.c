@@ -197,6 +197,75 @@ void orc_label_exact(const short *seeds, short *labels, int n) {
     free(c);
 }
 
+/* Rule A2 for the rows [r0, r1) of an n x n grid, from a site LIST instead of a dense seed map (sizes where
+ * the dense maps do not fit a test: 16384^2, 32768^2).  Column candidates come from the sorted site rows of
+ * every column; the row pass is the stack of orc_label_exact.  labels: (r1-r0) * n short2. */
+void orc_label_band(const short *sx, const short *sy, int K, int n, int r0, int r1, short *labels) {
+    int *start = (int *)calloc((size_t)n + 1, sizeof(int));
+    short *rows = (short *)malloc(sizeof(short) * (size_t)(K > 0 ? K : 1));
+    for (int k = 0; k < K; ++k) start[sx[k] + 1]++;
+    for (int x = 0; x < n; ++x) start[x + 1] += start[x];
+    {   /* counting sort by column, then by row inside the column */
+        int *fill = (int *)malloc(sizeof(int) * (size_t)n);
+        memcpy(fill, start, sizeof(int) * (size_t)n);
+        for (int k = 0; k < K; ++k) rows[fill[sx[k]]++] = sy[k];
+        free(fill);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int x = 0; x < n; ++x) {
+            short *a = rows + start[x];
+            int m = start[x + 1] - start[x];
+            for (int i = 1; i < m; ++i) { short v = a[i]; int j = i - 1; while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; } a[j + 1] = v; }
+        }
+    }
+    const int nr = r1 - r0;
+    short *c = (short *)malloc(sizeof(short) * (size_t)nr * n);
+#pragma omp parallel for schedule(static)
+    for (int x = 0; x < n; ++x) {
+        const short *a = rows + start[x];
+        const int m = start[x + 1] - start[x];
+        int p = 0; /* a[p-1] = largest row <= Y, a[p] = smallest row > Y */
+        while (p < m && a[p] <= r0) ++p;
+        for (int Y = r0; Y < r1; ++Y) {
+            while (p < m && a[p] <= Y) ++p;
+            const int U = p > 0 ? a[p - 1] : MARK, D = p < m ? a[p] : MARK;
+            c[(size_t)(Y - r0) * n + x] = (short)choose_col(U, D, Y);
+        }
+    }
+#pragma omp parallel
+    {
+        int *ex = (int *)malloc(sizeof(int) * n);
+        long long *eH = (long long *)malloc(sizeof(long long) * n);
+        long long *eS = (long long *)malloc(sizeof(long long) * n);
+#pragma omp for schedule(static)
+        for (int Y = r0; Y < r1; ++Y) {
+            const short *cr = c + (size_t)(Y - r0) * n;
+            short *out = labels + 2 * (size_t)(Y - r0) * n;
+            int top = 0;
+            for (int x = 0; x < n; ++x) {
+                int cy = cr[x];
+                if (cy == MARK) continue;
+                long long g = cy - Y, H = (long long)x * x + g * g, B = 0;
+                while (top > 0) {
+                    B = floordiv(H - eH[top - 1], 2ll * (x - ex[top - 1]));
+                    if (top > 1 && B <= eS[top - 1]) --top; else break;
+                }
+                if (top > 0 && B >= n - 1) continue;
+                ex[top] = x; eH[top] = H; eS[top] = (top > 0) ? B : -(1ll << 40);
+                ++top;
+            }
+            int e = 0;
+            for (int X = 0; X < n; ++X) {
+                if (top == 0) { out[2 * X] = MARK; out[2 * X + 1] = MARK; continue; }
+                while (e + 1 < top && eS[e + 1] < X) ++e;
+                out[2 * X] = (short)ex[e];
+                out[2 * X + 1] = cr[ex[e]];
+            }
+        }
+        free(ex); free(eH); free(eS);
+    }
+    free(c); free(rows); free(start);
+}
+
 /* Jump flooding (north_star's kernel family; NOT in the reference).
  * Schedule: nsteps step sizes, each pass reads the 3x3 stencil at +-k from the
  * previous pass's buffer (ping-pong).  Candidate order is fixed (dy=-k,0,+k outer,

@@ -44,6 +44,8 @@ def lib():
     p, i, d = C.c_void_p, C.c_int, C.c_double
     L.srm_last_error.restype = C.c_char_p
     L.srm_version.restype = i
+    L.srm_launch_count.restype = C.c_longlong
+    L.srm_launch_count.argtypes = []
     L.srm_gcvt.argtypes = [p, p, p, i, i, i, p]
     L.srm_discretize.argtypes = [p, p, i, p, i, p, d, i]
     L.srm_release_cache.argtypes = []
@@ -77,12 +79,13 @@ def lib():
     L.srm_run.argtypes = [p, i, i, p]
     L.srm_get_state.argtypes = [p, p]
     L.srm_debug_counts.argtypes = [p, C.POINTER(C.c_longlong), C.POINTER(i)]
+    L.srm_debug_get.argtypes = [p, i, C.POINTER(C.c_longlong)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
                  "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
-                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_get_labels", "srm_label_jfa"):
+                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -386,6 +389,13 @@ class Context:
         runs, ovf = C.c_longlong(), C.c_int()
         _ck(lib().srm_debug_counts(self._h, C.byref(runs), C.byref(ovf)))
         return runs.value, ovf.value
+
+    def debug_get(self, which):
+        """Statistics counter `which` of the band kernel (option dbg_stats = 1): 0/1/2 band-list max/sum/bands,
+        6 = warps that took Phase A's staging-overflow fallback."""
+        v = C.c_longlong()
+        _ck(lib().srm_debug_get(self._h, int(which), C.byref(v)))
+        return v.value
 
     def get_labels(self, out=None):
         rows = self.row1 - self.row0

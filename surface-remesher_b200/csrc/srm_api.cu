@@ -38,6 +38,8 @@ static int fail(int code, const char *fmt, ...) {
                         __LINE__);                                                                       \
     } while (0)
 
+long long g_srm_launches = 0;
+extern "C" long long srm_launch_count(void) { return __sync_fetch_and_add(&g_srm_launches, 0ll); }
 extern "C" const char *srm_last_error(void) { return g_err; }
 extern "C" int srm_version(void) { return 100; }
 
@@ -101,6 +103,7 @@ struct srm_ctx {
     int *edge = nullptr;       // row bands: per column, nearest site row above / below the band (2n ints)
     int dbg_stats = 0;
     bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
+    bool claim_dirty = false;  // an update has written dedupe claims that the next labelling has not reset yet
     SrmCtl *ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
@@ -127,6 +130,9 @@ static int alloc_sites(srm_ctx *c, int K) {
         c->cur = 0;
         return SRM_OK;
     }
+    if (c->world > 1)   // peer mappings (srm_p2p_connect) and the NCCL element count refer to the current buffers
+        return fail(SRM_ERR_STATE, "site set of %d entries exceeds the capacity %d the row-band collective was set up "
+                                   "with: destroy the band contexts and reconnect", K, c->Kcap);
     for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
     if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
     if (c->newpos) { cudaFree(c->newpos); c->newpos = nullptr; }
@@ -146,6 +152,11 @@ static int alloc_sites(srm_ctx *c, int K) {
 }
 
 static int reset_ctl(srm_ctx *c, int K) {
+    if (c->claim_dirty) {   // an update wrote claims that no labelling has reset since (k_bits resets them at the live
+        srm_launch_fill_int(c->stream, c->claim, c->N, INT_MAX);   // sites): a new site set must not see them
+        CK(cudaGetLastError());
+        c->claim_dirty = false;
+    }
     SrmCtl h;
     memset(&h, 0, sizeof(h));
     h.K = K; h.nlive = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
@@ -334,8 +345,20 @@ extern "C" int srm_p2p_connect(srm_ctx *c, const void *blobs, int rank, int worl
     return SRM_OK;
 }
 
+// A row band (not the whole grid) updates from partial sums unless a collective is bound: refuse instead of diverging.
+static int require_collective(srm_ctx *c, const char *who) {
+    if (c->p2p || c->comm) return SRM_OK;
+    if (c->world > 1)
+        return fail(SRM_ERR_STATE, "%s: world = %d but neither the peer-memory nor the NCCL all-reduce is connected", who, c->world);
+    if (c->g.row0 > 0 || c->g.row1 < c->g.n)
+        return fail(SRM_ERR_STATE, "%s: rows [%d,%d) of %d are a row band; connect srm_p2p_connect / srm_nccl_init first, or "
+                                   "step it with srm_label_accumulate / srm_acc_buffer / srm_update", who, c->g.row0, c->g.row1, c->g.n);
+    return SRM_OK;
+}
+
 static int allreduce_acc(srm_ctx *c) {
-    if (!c->comm || c->p2p) return SRM_OK;  // peer-memory mode: the update kernel pulls the partial sums itself
+    if (c->p2p) return SRM_OK;   // peer-memory mode: the update kernel pulls the partial sums itself
+    if (!c->comm) return require_collective(c, "all-reduce");
     int e = g_nccl.AllReduce(c->acc, c->acc, 4 * (size_t)c->Kcap + 4, /*ncclFloat64*/ 8, /*ncclSum*/ 0, c->comm, c->stream);
     if (e) return fail(SRM_ERR_CUDA, "ncclAllReduce: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(e) : "error");
     return SRM_OK;
@@ -414,6 +437,12 @@ extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device
 extern "C" int srm_set_sites(srm_ctx *c, const int *packed_xy, int num, int on_device) {
     if (!c || (!packed_xy && num > 0) || num < 0) return fail(SRM_ERR_ARG, "srm_set_sites: bad argument");
     CK(cudaSetDevice(c->device));
+    if (!on_device)   // the kernels index the bitmap and the site-id map with these coordinates
+        for (int i = 0; i < num; ++i) {
+            const int v = packed_xy[i], x = srm_x(v), y = srm_y(v);
+            if (v != SRM_SENT && (x < 0 || y < 0 || x >= c->g.n || y >= c->g.n))
+                return fail(SRM_ERR_ARG, "srm_set_sites: site %d = (%d,%d) outside the %d x %d grid", i, x, y, c->g.n, c->g.n);
+        }
     int rc = alloc_sites(c, num);
     if (rc) return rc;
     if (num > 0)
@@ -431,6 +460,9 @@ static int fetch_ctl(srm_ctx *c, SrmCtl *h) {
     CK(cudaStreamSynchronize(c->stream));
     c->it_host = h->it;  // iterations enqueued after a device-side stop were no-ops
     c->stopped = h->stop != 0;
+    if (h->p2p_timeout)
+        return fail(SRM_ERR_CUDA, "row-band all-reduce: a peer never signalled iteration %d (rank %d of %d gave up waiting); "
+                                  "the site lists are no longer consistent", h->it + 1, c->rank, c->world);
     return SRM_OK;
 }
 
@@ -483,6 +515,18 @@ extern "C" int srm_debug_counts(srm_ctx *c, long long *total_runs, int *overflow
         fprintf(stderr, "[srm dbg] band list: max %d mean %.1f (%d bands) | row survivors: max %d mean %.1f (%d rows)\n",
                 hc.dbg[0], hc.dbg[2] ? (double)hc.dbg[1] / hc.dbg[2] : 0.0, hc.dbg[2], hc.dbg[3],
                 hc.dbg[5] ? (double)hc.dbg[4] / hc.dbg[5] : 0.0, hc.dbg[5]);
+    return SRM_OK;
+}
+
+// Statistics counter SrmCtl::dbg[which] (collected while the option "dbg_stats" is on): 0 max / 1 sum of the band-list
+// length, 2 bands, 6 warps that took the staging-overflow fallback of the band kernel's Phase A.
+extern "C" int srm_debug_get(srm_ctx *c, int which, long long *value) {
+    if (!c || !value || which < 0 || which >= 8) return fail(SRM_ERR_ARG, "srm_debug_get: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int v = 0;
+    CK(cudaMemcpy(&v, &c->ctl->dbg[which], sizeof(int), cudaMemcpyDeviceToHost));
+    *value = v;
     return SRM_OK;
 }
 
@@ -560,6 +604,7 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
     CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
                       acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
     if (accumulate) srm_launch_signal(c->stream, c->ctl, peers_of(c, it), respect_stop);
+    c->claim_dirty = false;   // k_bits reset the claims at every live site
     return SRM_OK;
 }
 
@@ -619,17 +664,22 @@ extern "C" int srm_update(srm_ctx *c) {
     int rc = require_ready(c, "srm_update", true);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
+    // (stepwise mode with world > 1 and no bound collective is the caller-side all-reduce of ShardedLloyd.step:
+    //  srm_acc_buffer hands out the sums, so nothing to check here)
     const int buf = current_buffer(c);
     srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
                       c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, (c->it_host % 10) == 0, 0, 0, peers_of(c, c->it_host));
     CK(cudaGetLastError());
     c->labelled = false;
+    c->claim_dirty = true;
     c->it_host += 1;
     return SRM_OK;
 }
 
 extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     int rc = require_ready(c, "srm_iterate", true);
+    if (rc) return rc;
+    rc = require_collective(c, "srm_iterate");
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
     if (c->stopped) return SRM_OK;
@@ -647,6 +697,7 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     CK(cudaGetLastError());
     c->it_host = it;
     c->labelled = false;
+    c->claim_dirty = true;
     if (stop_rule) {  // the device may have stopped early: resynchronise the host mirror
         SrmCtl h;
         rc = fetch_ctl(c, &h);
@@ -662,6 +713,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
     int rc = require_ready(c, "srm_iterate_profiled", true);
     if (rc) return rc;
     if (!stage_ms || iters <= 0) return fail(SRM_ERR_ARG, "srm_iterate_profiled: bad argument");
+    rc = require_collective(c, "srm_iterate_profiled");
+    if (rc) return rc;
     CK(cudaSetDevice(c->device));
     for (int k = 0; k < 6; ++k) stage_ms[k] = 0;
     if (c->stopped) return SRM_OK;
@@ -712,6 +765,7 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
     for (auto &e : ev) cudaEventDestroy(e);
     c->it_host = it;
     c->labelled = false;
+    c->claim_dirty = true;
     SrmCtl h;
     return fetch_ctl(c, &h);
 }

@@ -286,9 +286,23 @@ __device__ __forceinline__ bool sitetab_add(const SiteTab &T, unsigned v, double
 }
 #endif
 
+// Measurement code is compiled in only with -DSRM_MEASURE (tools/prof_band.py, tools/ablate_band.py build that variant):
+// per-phase clock64 counters (dbg & 1) and the ablation switches of the accumulation (dbg & 2: no atomics, dbg & 4:
+// synthetic site ids, dbg & 8: no prefix loads).  The default build keeps only the band-list statistics below.
+#ifdef SRM_MEASURE
 #define PROF_T0() long long t0__ = (dbg & 1) ? clock64() : 0
 #define PROF_ADD(slot) do { if (dbg & 1) { long long t1__ = clock64(); if (lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(t1__ - t0__)); t0__ = t1__; } } while (0)
 #define PROF_CNT(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->prof[slot], (unsigned long long)(v)); } while (0)
+#define ABL(bit) (dbg & (bit))
+#else
+#define PROF_T0() do { } while (0)
+#define PROF_ADD(slot) do { } while (0)
+#define PROF_CNT(slot, v) do { } while (0)
+#define ABL(bit) 0
+#endif
+// statistics counters in SrmCtl::dbg (option "dbg_stats"): [0] max / [1] sum of the band-list length, [2] bands,
+// [6] warps that took the staging-overflow fallback of Phase A
+#define SRM_STAT_ADD(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->dbg[slot], (int)(v)); } while (0)
 
 template <int RPW, int C, int GS0, int GS1>
 __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
@@ -326,14 +340,13 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     }
 #endif
     double e_loc = 0;
-    __shared__ int stage_ovf;
 #if BAND_PERSIST
     // Persistent form: the grid holds as many CTAs as are resident at once and every CTA takes bands from a ticket
     // until none is left, so an SM keeps its full complement of CTAs until the very end (no partial second wave).
     __shared__ int s_band;
     for (;;) {
         __syncthreads();   // every warp is done with the previous band's shared memory
-        if (t == 0) { s_band = atomicAdd(&ctl->band_ticket, 1); stage_ovf = 0; }
+        if (t == 0) s_band = atomicAdd(&ctl->band_ticket, 1);
         __syncthreads();
         const int bi = s_band;
         if (bi >= nbands) break;
@@ -341,7 +354,6 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     {
         const int bi = blockIdx.x;
         (void)nbands;
-        if (t == 0) stage_ovf = 0;
 #endif
     const int rb = bi * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
 #if BAND_SITETAB > 0
@@ -394,7 +406,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         } else staged = false;
         mycount += tot;
     }
-    if (lane == 0) { wcnt[w] = mycount; if (!staged) stage_ovf = 1; }
+    if (lane == 0) wcnt[w] = mycount;
     __syncthreads();
     int mb = 0, wbase = 0;
 #pragma unroll
@@ -408,11 +420,15 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         return;
 #endif
     }
-    if (!stage_ovf) {
-        // ---- assemble the band list: copy the staged entries to their place
+    // Every warp assembles its own section [wbase, wbase + mycount) of the band list, so the choice between the two
+    // forms below is warp-local (`staged` is warp-uniform): no flag is shared between warps.
+    if (staged) {
+        // ---- copy the staged entries to their place
         for (int i = lane; i < mycount; i += 32) L[wbase + i] = stage[i];
     } else {
-        // ---- fallback (a warp's staging area overflowed): recompute the live columns and write the list in order
+        // ---- fallback (this warp's staging area overflowed): recompute its live columns from the masks it wrote in
+        // pass 1 and write the list in order
+        SRM_STAT_ADD(6, 1);
         int base = wbase;
         for (int b0 = bw0; b0 < bw1; b0 += 32) {
             const int b = b0 + lane;
@@ -540,12 +556,12 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 int id[2];
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {  // all loads of both chunks first
-                    pb[q] = (st[q].owned && !(dbg & 8)) ? p2[(size_t)st[q].B * SRM_PFX_TILE] : make_double2(1, 1);
+                    pb[q] = (st[q].owned && !ABL(8)) ? p2[(size_t)st[q].B * SRM_PFX_TILE] : make_double2(1, 1);
                     xb[q] = (st[q].owned && want_energy) ? pxx[(size_t)st[q].B * SRM_PFX_TILE] : 0;
 #if BAND_SITETAB > 0
                     id[q] = -1;   // looked up only by the runs that find no table slot
 #else
-                    id[q] = st[q].owned ? ((dbg & 4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
+                    id[q] = st[q].owned ? (ABL(4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
 #endif
                 }
 #pragma unroll
@@ -566,13 +582,16 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                         if (id[q] >= 0) {
 #else
                         double *a = acc + 4 * (size_t)id[q];
-                        if (!(dbg & 2)) {
+                        if (!ABL(2)) {
 #endif
                             atomicAdd(a, W);
                             atomicAdd(a + 1, X);
                             atomicAdd(a + 2, (double)Y * W);
                             reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id[q]] = 1;
-                        } else if (W == -1.5) a[3] = X;
+                        }
+#ifdef SRM_MEASURE
+                        else if (W == -1.5) a[3] = X;   // keeps the loads alive when the atomics are ablated
+#endif
                         if (want_energy) e_loc += (xb[q] - xa) - 2.0 * (double)xx[q] * X + (double)(HH[q]) * W;
                     }
                 }
@@ -662,9 +681,11 @@ cudaError_t srm_band_setup(int n) {
 // more than Phase A for a latency-bound kernel; 16 stays selectable for experiments (SRM_BAND_RPW=2).
 static int band_rpw(int nrows) {
     (void)nrows;
-    const char *env = getenv("SRM_BAND_RPW");
-    if (env && (env[0] == '1' || env[0] == '2')) return env[0] - '0';
-    return 1;
+    static const int rpw = []() {   // read once per process, not per launch
+        const char *env = getenv("SRM_BAND_RPW");
+        return (env && (env[0] == '1' || env[0] == '2')) ? env[0] - '0' : 1;
+    }();
+    return rpw;
 }
 
 template <int RPW, int C>
@@ -684,7 +705,7 @@ static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, 
         grid = min(nbands, max(1, per_sm[RPW - 1][ci]) * max(1, sms));
     }
 #endif
-    k_band<RPW, C, BAND_GS0, BAND_GS1><<<grid, BAND_NT, smem, st>>>(
+    SRM_COUNT(), k_band<RPW, C, BAND_GS0, BAND_GS1><<<grid, BAND_NT, smem, st>>>(
         bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
         respect_stop, dbg, nbands);
 }

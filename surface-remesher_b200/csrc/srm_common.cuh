@@ -84,6 +84,11 @@ struct SrmPeers {
     int parity = 0;
 };
 
+// Kernel launches issued by this library since it was loaded (srm_launch_count(); bench.py reports the difference
+// over its timed region as gpu_launches).  Every `<<<>>>` site counts itself: SRM_COUNT(), k_x<<<...>>>(...).
+extern long long g_srm_launches;
+#define SRM_COUNT() ((void)__sync_fetch_and_add(&g_srm_launches, 1ll))
+
 // ---- launchers (host), one per pipeline stage; all asynchronous on `st`.
 struct SrmGrid {           // geometry of one context
     int n, row0, row1;

@@ -51,7 +51,7 @@ void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, i
         cudaMemsetAsync(edge, 0x80, (size_t)n * sizeof(int), st);
         cudaMemsetAsync(edge + n, 0x7f, (size_t)n * sizeof(int), st);
     }
-    k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop, row0, row1, edge);
+    SRM_COUNT(), k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop, row0, row1, edge);
 }
 
 __device__ __forceinline__ int edge_top(const int *edge, int x) {
@@ -187,16 +187,16 @@ void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, s
     const int wps = (nw % 8) ? 0 : nw / 8;
     dim3 grid(n / 32), block(32, 8);
     if (wps > 32 && nw % 32 == 0) {   // long columns: 32 segments, looped
-        k_carry_loop<32><<<grid, dim3(32, 32), 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, nw / 32, e);
+        SRM_COUNT(), k_carry_loop<32><<<grid, dim3(32, 32), 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, nw / 32, e);
         return;
     }
-#define CARRY_CASE(W) if (wps == W) { k_carry<W, 8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); return; }
+#define CARRY_CASE(W) if (wps == W) { SRM_COUNT(), k_carry<W, 8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); return; }
     CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
     if (wps > 0) {   // other band heights (work-balanced row bands): 8 segments, looped
-        k_carry_loop<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, wps, e);
+        SRM_COUNT(), k_carry_loop<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, wps, e);
         return;
     }
-    k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e);
+    SRM_COUNT(), k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e);
 #undef CARRY_CASE
 }
 
@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
+    __shared__ int row_total;   // runs of the row (its own word: wtot[] is still being read by slower warps)
     if (respect_stop && ctl->stop) return;
     EnvSmem s;
     s.x = (unsigned short *)smem_raw;
@@ -325,11 +326,11 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
             for (int k = 0; k < w; ++k) off += wtot[k];
             int2 *out = rle + (size_t)r * n + off;
             for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.x[i], s.c[i]), (int)s.S[i] + 1);
-            if (t == ROW_NT - 1) { rle_cnt[r] = off + cnt; wtot[0] = off + cnt; }
+            if (t == ROW_NT - 1) { rle_cnt[r] = off + cnt; row_total = off + cnt; }
         }
         __syncthreads();
         if (accumulate && w == 0) {
-            double e_loc = acc_row(rle + (size_t)r * n, wtot[0], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, Y, acc,
+            double e_loc = acc_row(rle + (size_t)r * n, row_total, P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, Y, acc,
                                    Kcap, want_energy, lane);
             if (want_energy) {
                 e_loc = warp_sum(e_loc);
@@ -358,7 +359,7 @@ cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *u
                            const int *idmap, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
                            int respect_stop) {
     const int grid = rows ? 148 : g.nrows();
-    k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, P2,
+    SRM_COUNT(), k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, P2,
                                                      PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop);
     return cudaGetLastError();
 }
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(EXP_NT) k_expand(const int2 *__restrict__ rle,
 
 cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels) {
     size_t sm = (size_t)g.n * sizeof(int);
-    k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, rle_cnt, g.n, labels);
+    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, rle_cnt, g.n, labels);
     return cudaGetLastError();
 }
 
@@ -470,7 +471,7 @@ __global__ void __launch_bounds__(256) k_jfa(const int *__restrict__ in, int *__
 
 void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step) {
     size_t groups = (size_t)n * n / 4;
-    k_jfa<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(in, out, n, step);
+    SRM_COUNT(), k_jfa<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(in, out, n, step);
 }
 
 __global__ void k_scatter_sites(const int *__restrict__ sites, const SrmCtl *__restrict__ ctl, int n, int *map) {
@@ -481,7 +482,7 @@ __global__ void k_scatter_sites(const int *__restrict__ sites, const SrmCtl *__r
 }
 
 void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map) {
-    if (Kcap > 0) k_scatter_sites<<<(Kcap + 255) / 256, 256, 0, st>>>(sites, ctl, n, map);
+    if (Kcap > 0) SRM_COUNT(), k_scatter_sites<<<(Kcap + 255) / 256, 256, 0, st>>>(sites, ctl, n, map);
 }
 
 __global__ void k_fill_int(int4 *p, size_t count4, int value) {
@@ -495,5 +496,5 @@ void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value) {
     size_t c4 = count / 4;
     unsigned blocks = (unsigned)((c4 + 255) / 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    k_fill_int<<<blocks, 256, 0, st>>>(reinterpret_cast<int4 *>(p), c4, value);
+    SRM_COUNT(), k_fill_int<<<blocks, 256, 0, st>>>(reinterpret_cast<int4 *>(p), c4, value);
 }

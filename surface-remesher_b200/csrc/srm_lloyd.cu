@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ den
 }
 
 void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX) {
-    k_prefix<<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
+    SRM_COUNT(), k_prefix<<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
 }
 
 // ------------------------------------------------------------------ per-run accumulation
@@ -98,7 +98,7 @@ void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const 
                     const SrmCtl *ctl, int want_energy, int respect_stop) {
     const int rows_per_block = ACC_NT / 32;
     const int grid = rows ? 148 : (g.nrows() + rows_per_block - 1) / rows_per_block;
-    k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
+    SRM_COUNT(), k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
                                    want_energy, respect_stop);
 }
 
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(1024) k_scan_counts(const int *__restrict__ cn
 }
 
 void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out) {
-    k_scan_counts<<<1, 1024, 0, st>>>(cnt, off, nb, total_out);
+    SRM_COUNT(), k_scan_counts<<<1, 1024, 0, st>>>(cnt, off, nb, total_out);
 }
 
 // ------------------------------------------------------------------ site update
@@ -157,7 +157,7 @@ __global__ void k_signal(SrmCtl *ctl, SrmPeers p, int respect_stop) {
 }
 
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop) {
-    if (peers.world > 1) k_signal<<<1, 32, 0, st>>>(ctl, peers, respect_stop);
+    if (peers.world > 1) SRM_COUNT(), k_signal<<<1, 32, 0, st>>>(ctl, peers, respect_stop);
 }
 
 __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const float *__restrict__ density,
@@ -170,10 +170,15 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
             for (int q = 0; q < peers.world; ++q) {
                 long long spins = 0;
                 while (ld_volatile_int(peers.flags_local + q) < target)
-                    if (++spins > (1ll << 28)) { ctl->p2p_timeout = 1; break; }  // fail-safe: never hang the GPU
+                    if (++spins > (1ll << 28)) {   // fail-safe: never hang the GPU.  The sums are incomplete: stop the
+                        ctl->p2p_timeout = 1;      // loop (every later kernel returns at once) and let the host
+                        ctl->stop = 1;             // report it (fetch_ctl -> SRM_ERR_CUDA)
+                        break;
+                    }
             }
         }
         __syncthreads();
+        if (ctl->p2p_timeout) return;   // a peer never arrived: do not update from partial sums
     }
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
                                                            int respect_stop, SrmPeers peers) {
     __shared__ int is_last;
     if (respect_stop && ctl->stop) return;  // set only by a previous launch's last block
+    if (ctl->p2p_timeout) return;           // k_update_pos gave up waiting for a peer: leave the sites as they are
     const int id = blockIdx.x * UPD_NT + threadIdx.x;
     int alive = 0;
     if (id < ctl->K) {
@@ -305,8 +311,8 @@ void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, dou
                        int stop_rule, int respect_stop, SrmPeers peers) {
     // acc: single GPU: the accumulator buffer; peers: the BASE of this rank's buffer pair
     const int k1 = Kcap > 0 ? Kcap : 1;
-    k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop, peers);
-    k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
+    SRM_COUNT(), k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop, peers);
+    SRM_COUNT(), k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
                                                                      stop_rule, respect_stop, peers);
 }
 
@@ -327,7 +333,7 @@ __global__ void __launch_bounds__(256) k_density_scale(const float *__restrict__
 }
 
 void srm_launch_density_scale(cudaStream_t st, const float *in, float *out, int s) {
-    k_density_scale<<<dim3((s + 31) / 32, (s + 7) / 8), 256, 0, st>>>(in, out, s);
+    SRM_COUNT(), k_density_scale<<<dim3((s + 31) / 32, (s + 7) / 8), 256, 0, st>>>(in, out, s);
 }
 
 // kernelZoomIn on the site list: (x, y) -> (2x, 2y); holes stay holes.
@@ -339,7 +345,7 @@ __global__ void k_zoom_sites(const int *__restrict__ in, int *__restrict__ out, 
 }
 
 void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K) {
-    if (K > 0) k_zoom_sites<<<(K + 255) / 256, 256, 0, st>>>(in, out, K);
+    if (K > 0) SRM_COUNT(), k_zoom_sites<<<(K + 255) / 256, 256, 0, st>>>(in, out, K);
 }
 
 // ------------------------------------------------------------------ dense seed map -> site list
@@ -396,9 +402,9 @@ void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, i
     const size_t n4 = N / 4;
     const int nb = (int)((n4 + SFM_NT - 1) / SFM_NT);
     if (count_only) {
-        k_sites_count<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockcnt);
-        k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, total_out);
+        SRM_COUNT(), k_sites_count<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockcnt);
+        SRM_COUNT(), k_scan_counts<<<1, 1024, 0, st>>>(blockcnt, blockoff, nb, total_out);
     } else {
-        k_sites_write<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockoff, sites_out);
+        SRM_COUNT(), k_sites_write<<<nb, SFM_NT, 0, st>>>(reinterpret_cast<const int4 *>(site_map), n4, blockoff, sites_out);
     }
 }

@@ -122,17 +122,17 @@ cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int
     cudaMemsetAsync(off, 0, sizeof(int) * ntiles, st);
     int total = 0;
     if (num_tri > 0) {
-        k_tri_bin<<<(num_tri + 127) / 128, 128, 0, st>>>(pts, tri, num_tri, scale, n, cnt, nullptr, nullptr);
+        SRM_COUNT(), k_tri_bin<<<(num_tri + 127) / 128, 128, 0, st>>>(pts, tri, num_tri, scale, n, cnt, nullptr, nullptr);
         srm_launch_scan_counts(st, cnt, off, ntiles, total_d);
         cudaMemcpyAsync(&total, total_d, sizeof(int), cudaMemcpyDeviceToHost, st);
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto done;
         if ((e = cudaMalloc(&list, sizeof(int) * (size_t)(total > 0 ? total : 1))) != cudaSuccess) goto done;
         cudaMemsetAsync(cnt, 0, sizeof(int) * ntiles, st);
-        k_tri_bin<<<(num_tri + 127) / 128, 128, 0, st>>>(pts, tri, num_tri, scale, n, cnt, off, list);
+        SRM_COUNT(), k_tri_bin<<<(num_tri + 127) / 128, 128, 0, st>>>(pts, tri, num_tri, scale, n, cnt, off, list);
     }
     {
         dim3 grid(nt, nt), block(RT_TILE, RT_TILE);
-        k_raster<<<grid, block, 0, st>>>(pts, wt, tri, off, cnt, list, scale, n, density);
+        SRM_COUNT(), k_raster<<<grid, block, 0, st>>>(pts, wt, tri, off, cnt, list, scale, n, density);
     }
     e = cudaStreamSynchronize(st);
 done:

@@ -152,7 +152,7 @@ cudaError_t srm_locator_build(cudaStream_t st, const double *pts_host, int P, co
     cudaMemsetAsync(L->cnt, 0, sizeof(int) * nc, st);
     cudaMemsetAsync(L->off, 0, sizeof(int) * nc, st);
     if (T > 0) {
-        k_loc_bin<<<(T + 127) / 128, 128, 0, st>>>(pts_dev, tri_dev, T, L->g, L->cnt, nullptr, nullptr);
+        SRM_COUNT(), k_loc_bin<<<(T + 127) / 128, 128, 0, st>>>(pts_dev, tri_dev, T, L->g, L->cnt, nullptr, nullptr);
         srm_launch_scan_counts(st, L->cnt, L->off, nc, total_d);
         cudaMemcpyAsync(&total, total_d, sizeof(int), cudaMemcpyDeviceToHost, st);
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto fail;
@@ -160,7 +160,7 @@ cudaError_t srm_locator_build(cudaStream_t st, const double *pts_host, int P, co
     if ((e = cudaMalloc(&L->list, sizeof(int) * (size_t)(total > 0 ? total : 1))) != cudaSuccess) goto fail;
     if (T > 0) {
         cudaMemsetAsync(L->cnt, 0, sizeof(int) * nc, st);
-        k_loc_bin<<<(T + 127) / 128, 128, 0, st>>>(pts_dev, tri_dev, T, L->g, L->cnt, L->off, L->list);
+        SRM_COUNT(), k_loc_bin<<<(T + 127) / 128, 128, 0, st>>>(pts_dev, tri_dev, T, L->g, L->cnt, L->off, L->list);
     }
     if ((e = cudaGetLastError()) != cudaSuccess) goto fail;
     cudaFree(total_d);
@@ -175,13 +175,13 @@ fail:
 cudaError_t srm_locator_query(cudaStream_t st, const SrmLocator *L, const double *pts_dev, const int *tri_dev,
                               const double *qxy_dev, const int *centroid_of_dev, int Q, int *face_dev, double *w_dev) {
     if (Q > 0)
-        k_locate<<<(Q + LOC_NT - 1) / LOC_NT, LOC_NT, 0, st>>>(pts_dev, tri_dev, L->g, L->off, L->cnt, L->list, qxy_dev,
+        SRM_COUNT(), k_locate<<<(Q + LOC_NT - 1) / LOC_NT, LOC_NT, 0, st>>>(pts_dev, tri_dev, L->g, L->off, L->cnt, L->list, qxy_dev,
                                                                centroid_of_dev, Q, face_dev, w_dev);
     return cudaGetLastError();
 }
 
 cudaError_t srm_launch_lift(cudaStream_t st, const int *tri_dev, const double *pts3d_dev, const int *face_dev,
                             const double *w_dev, int Q, double *out_dev) {
-    if (Q > 0) k_lift<<<(Q + 127) / 128, 128, 0, st>>>(tri_dev, pts3d_dev, face_dev, w_dev, Q, out_dev);
+    if (Q > 0) SRM_COUNT(), k_lift<<<(Q + 127) / 128, 128, 0, st>>>(tri_dev, pts3d_dev, face_dev, w_dev, Q, out_dev);
     return cudaGetLastError();
 }

@@ -36,6 +36,7 @@ def lib():
         L.orc_random_points.restype = C.c_longlong
         L.orc_label_brute.argtypes = [p, p, C.c_int]
         L.orc_label_exact.argtypes = [p, p, C.c_int]
+        L.orc_label_band.argtypes = [p, p, C.c_int, C.c_int, C.c_int, C.c_int, p]
         L.orc_label_jfa.argtypes = [p, p, C.c_int, p, C.c_int]
         L.orc_centroid.argtypes = [p, p, C.c_int, p, p, p]
         L.orc_energy.argtypes = [p, p, C.c_int]
@@ -96,6 +97,15 @@ def label_exact(seeds):
     s = np.ascontiguousarray(seeds, np.int16)
     out = np.empty_like(s)
     lib().orc_label_exact(_p(s), _p(out), n)
+    return out
+
+
+def label_band(sites_xy, n, r0, r1):
+    """Rule A2 for rows [r0, r1) from a site list (K,2) int16 (x,y): labels int16[r1-r0, n, 2]."""
+    xy = np.asarray(sites_xy, np.int16)
+    sx = np.ascontiguousarray(xy[:, 0]); sy = np.ascontiguousarray(xy[:, 1])
+    out = np.empty((r1 - r0, n, 2), np.int16)
+    lib().orc_label_band(_p(sx), _p(sy), len(sx), int(n), int(r0), int(r1), _p(out))
     return out
 
 

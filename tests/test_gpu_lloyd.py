@@ -28,24 +28,35 @@ def _packed_set(packed):
 
 @pytest.mark.parametrize("kind,n,k,omega", [("uniform", 256, 400, 2.0), ("c3", 512, 3000, 2.0), ("c3", 512, 3000, 1.37),
                                             ("uniform", 1024, 2000, 2.0), ("c3", 1024, 20000, 1.0),
-                                            ("c3", 2048, 10000, 2.0)])
+                                            ("c3", 2048, 10000, 2.0),
+                                            # BASELINE.json configs[1] and configs[2] at full size (the O(N) C oracle takes seconds)
+                                            ("uniform", 4096, 20000, 2.0), ("c3", 8192, 100000, 2.0),
+                                            ("c3", 8192, 100000, 1.21)])
 def test_single_step_teacher_forced(kind, n, k, omega):
+    """One Lloyd step from the same site map, compared with the oracle: labels, the updated site set, the energy.
+    Both forms of the accumulation are checked: the fused band kernel (the product loop, srm_label_accumulate) and the
+    separate per-run kernel (srm_label + srm_accumulate); above 2048^2 only the fused one (test time)."""
     import surface_remesher_b200 as S
     dens, mask, seeds = _case(kind, n, k)
-    with S.Context(n) as c:
-        c.set_density(dens); c.set_mask(mask); c.set_site_map(seeds)
-        c.set_omega(omega)
-        c.label()
-        lab = c.get_labels()
-        c.accumulate(True)
-        c.update()
-        got = _packed_set(c.get_sites())
-        st = c.state()
     elab, eout, e = O.lloyd_step(seeds, dens, mask, omega)
-    assert (lab != elab).sum() == 0
-    assert got == I.site_set(eout)
-    assert st["iterations"] == 1 and st["num_sites"] == len(got)
-    assert st["energy"] == np.float32(e) or abs(st["energy"] - e) / e < 1e-6
+    with S.Context(n) as c:
+        c.set_density(dens); c.set_mask(mask)
+        for fused in ([True, False] if n <= 2048 else [True]):
+            c.set_site_map(seeds)
+            c.set_omega(omega)
+            if fused:
+                c.label_accumulate(True)
+            else:
+                c.label()
+                c.accumulate(True)
+            lab = c.get_labels()
+            c.update()
+            got = _packed_set(c.get_sites())
+            st = c.state()
+            assert (lab != elab).sum() == 0
+            assert got == I.site_set(eout), fused
+            assert st["iterations"] == 1 and st["num_sites"] == len(got)
+            assert st["energy"] == np.float32(e) or abs(st["energy"] - e) / e < 1e-6
 
 
 @pytest.mark.parametrize("kind,n,k,iters,stop,robust", [("uniform", 256, 400, 60, True, False), ("c3", 512, 3000, 40, True, False),
