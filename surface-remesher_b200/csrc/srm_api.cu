@@ -589,7 +589,13 @@ extern "C" int srm_set_omega(srm_ctx *c, float omega) {
 // Inside the loop both agree until a stop; after a stop every kernel is a no-op, so using the
 // host parity for the (skipped) launches is harmless.  For calls outside the loop (final labelling)
 // the parity is read back from the device.
-static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy) {
+static int band_flags(srm_ctx *c, int respect_stop, int accumulate, int want_energy, int write_rle) {
+    return (accumulate ? SRM_BF_ACC : 0) | (want_energy ? SRM_BF_ENERGY : 0) | (respect_stop ? SRM_BF_STOP : 0) |
+           (write_rle ? SRM_BF_RLE : 0) | (c->p2p ? SRM_BF_TOUCH : 0);
+}
+
+// write_rle: the run-length rows are needed by srm_get_labels / srm_accumulate after this labelling (not inside the loop)
+static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy, int write_rle = 1) {
     const int buf = it & 1;
     double *acc = cur_acc(c, it);
     srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop, c->g.row0, c->g.row1, c->edge);
@@ -597,7 +603,8 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
         CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                           c->idmap, acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, c->dbg_stats));
+                           c->idmap, acc, c->Kcap, c->ctl, band_flags(c, respect_stop, accumulate, want_energy, write_rle),
+                           c->dbg_stats));
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
@@ -686,7 +693,7 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     int it = c->it_host;
     for (int i = 0; i < iters; ++i, ++it) {
         const int buf = it & 1, want_energy = (it % 10) == 0;
-        rc = label_with(c, it, 1, 1, want_energy);
+        rc = label_with(c, it, 1, 1, want_energy, /*write_rle=*/0);
         if (rc) return rc;
         rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
         if (rc) return rc;
@@ -732,7 +739,7 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {
             CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                               c->idmap, acc, c->Kcap, c->ctl, 1, want_energy, 1, c->dbg_stats));
+                               c->idmap, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats));
             rows = c->ovf_rows;
             count = &c->ctl->ovf;
         }

@@ -23,17 +23,22 @@
 // A band whose list exceeds CL entries, or a row whose envelope exceeds the buffer, is handed to the
 // robust path (k_row in srm_label.cu).
 //
-// Compile-time switches (defaults = the measured best; every alternative was A/B-measured on a B200 unless noted,
-// profiles/r1_kernel_log.md):
+// Output + accumulation (this round): the fp64 prefix pair at every run end and the run's site id are fetched with
+// cp.async (LDGSTS) into a ring of 32-run stages in the free part of the warp's own buffer, up to 4 stages (128 runs)
+// in flight per warp, and consumed from shared memory (neighbour = previous slot: no shuffles).  Round 1 issued 62
+// loads per warp and then stalled on them, five times per row.  Inside the loop the run-length rows are not written
+// (nothing reads them) and the per-site "touched" bytes only when a peer pulls the sums.
+//
+// Compile-time switches (defaults = the measured best; profiles/r1_kernel_log.md, profiles/r2_kernel_log.md):
 //   BAND_REACH    3   neighbouring 8-column blocks per side used by the band-level pruning (1: band list 1.7x longer)
-//   BAND_GS0/GS1  0   in-chunk Gauss-Seidel sweeps in round 0 / later rounds (fewer passes, same time)
 //   BAND_NCH      2   chunks in flight in the round loop (3, 4: no effect)
-//   BAND_LUT      0   reciprocal table instead of the float division in the breakpoint (512: exact, no effect)
 //   BAND_MINCTA   4   resident CTAs per SM the register allocation aims at; BAND_C8K / BAND_CL8K = buffer and band-list
 //                     capacities for n <= 8192 (5 or 6 CTAs per SM with smaller capacities: no gain / slower)
-//   BAND_PERSIST  0   persistent CTAs taking bands from a ticket (same results, 3 % slower)
-//   BAND_SITETAB  0   per-band shared-memory site table for the accumulation (written, NOT yet run on a GPU)
+//   BAND_NST      4   stages of the accumulation ring (1 = issue, wait, consume: the round-1 behaviour)
 //   SRM_PFX_TILE  1   (srm_common.cuh) rows interleaved in the fp64 prefix arrays (8: kernel -1 %, k_prefix slower)
+// Removed after round 1 (measured no gain, history in git): in-chunk Gauss-Seidel sweeps, reciprocal table for the
+// breakpoint division, persistent CTAs on a band ticket, the shared-memory site table with CAS-loop fp64 atomics
+// (an ATOMS.CAS costs more LSU time than the global RED it replaces, profiles/r2_kernel_log.md).
 // Variants are built into build/variants/ and compared in one process with tools/ab_inproc.py.
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
@@ -50,6 +55,10 @@
 #ifndef BAND_CL8K
 #define BAND_CL8K 2816     // band-list capacity (entries) for n <= 8192
 #endif
+#ifndef BAND_NST
+#define BAND_NST 4         // stages (of 32 runs) of the accumulation ring
+#endif
+#define BAND_STAGE_BYTES 896   // one stage: 32 x (16 B prefix pair + 8 B x^2 prefix + 4 B site id)
 
 struct Col8 {          // 8 consecutive columns of one band
     int U[8], D[8];    // nearest site row above / below the band (SRM_MARK if none)
@@ -100,14 +109,6 @@ __device__ __forceinline__ void load_col8(const uint32_t *__restrict__ bits, con
     unpack_col8<R>(load_raw8(bits, up, dn, o), j, k0, Y0, c);
 }
 
-template <int R>
-__device__ __forceinline__ int block_gmax(const uint32_t *__restrict__ bits, const short *__restrict__ up,
-                                          const short *__restrict__ dn, size_t o, int j, int k0, int Y0) {
-    Col8 c;
-    load_col8<R>(bits, up, dn, o, j, k0, Y0, c);
-    return c.M;
-}
-
 // A column with lower bound g = gmin is dead for the whole band when a candidate on its left beats it at its own
 // column x (then it loses for every X <= x) and a candidate on its right does too (every X >= x; strictly, the
 // smaller x wins ties).  TL / TR bound the squared distance of such candidates from above: the best of
@@ -154,31 +155,9 @@ __device__ __forceinline__ int breakpoint(int num, int den, int n) {
     return min(q, n - 1);
 }
 
-#ifndef BAND_PERSIST
-#define BAND_PERSIST 0 // 1: persistent CTAs that take bands from a ticket (grid = resident CTAs) instead of one CTA per band
-#endif
 #ifndef BAND_NCH
 #define BAND_NCH 2     // 31-element chunks in flight per iteration of the round loop over the element buffer
 #endif
-#ifndef BAND_LUT
-#define BAND_LUT 0     // > 0: neighbours less than BAND_LUT columns apart take their quotient estimate from a shared-memory
-#endif                 // table of reciprocals (one LDS + IMAD.HI) instead of I2F, I2F, MUFU.RCP, F2I (four XU-pipe operations)
-
-// Same result as breakpoint(num, 2 * gap, n).  lut[g] = floor(2^32 / (2g)) + 1, so umulhi(num, lut[g]) is the true
-// quotient or one more for 0 <= num < 2^31 (excess num * eps / 2^32 < 1/2); the +-1 fix-up below makes it exact.
-__device__ __forceinline__ int breakpoint_gap(int num, int gap, int n, const unsigned *__restrict__ lut) {
-#if BAND_LUT > 0
-    if ((unsigned)gap < (unsigned)BAND_LUT) {
-        const int den = 2 * gap;
-        int q = (int)__umulhi((unsigned)max(num, 0), lut[gap]);
-        q = min(q, n);
-        const int r = num - q * den;
-        q += (int)(r >= den) - (int)(r < 0);
-        return min(q, n - 1);
-    }
-#endif
-    return breakpoint(num, 2 * gap, n);
-}
 
 // Candidate of band-list entry i for row Y = Y0 + k: packed x | c << 16 and H = x^2 + (c - Y)^2.
 __device__ __forceinline__ void load_cand(const uint2 *__restrict__ L, int i, int Y0, int k, int Y, unsigned &v, int &x,
@@ -201,12 +180,12 @@ struct RoundStep {
     bool owned, keep;
 };
 __device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
-                                                int &carryB, const unsigned *__restrict__ lut) {
+                                                int &carryB) {
     RoundStep r;
     const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
     const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
     r.owned = valid && lane < 31;
-    r.B = validn ? breakpoint_gap(Hn - H, xn - x, n, lut) : n - 1;
+    r.B = validn ? breakpoint(Hn - H, 2 * (xn - x), n) : n - 1;
     r.Bc = __shfl_up_sync(0xffffffffu, r.B, 1);
     if (lane == 0) r.Bc = carryB;
     carryB = __shfl_sync(0xffffffffu, r.B, 30);
@@ -214,77 +193,28 @@ __device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigne
     return r;
 }
 
-// A dominance round over one chunk, with in-chunk Gauss-Seidel: after the parallel (Jacobi) test, lanes that
-// survive relink to their nearest surviving neighbours inside the chunk and are re-tested until the chunk is stable,
-// so a cascade of dominated elements inside 31 neighbours collapses in one pass instead of one pass per link.
-// Every test uses real candidates as dominators, so every drop is sound.  The carry handed to the next chunk is
-// the breakpoint of (last owned element, lookahead element) from the Jacobi step: a valid bound either way.
-template <int MAX_INNER>
-__device__ __forceinline__ bool chunk_round(bool valid, bool validn, unsigned v, int x, int H, int Y, int lane, int n,
-                                            int &carryB, const unsigned *__restrict__ lut) {
-    const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
-    const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y, Hn = xn * xn + gn * gn;
-    const bool owned = valid && lane < 31;
-    int B = validn ? breakpoint_gap(Hn - H, xn - x, n, lut) : n - 1;
-    int Bc = __shfl_up_sync(0xffffffffu, B, 1);
-    if (lane == 0) Bc = carryB;
-    carryB = __shfl_sync(0xffffffffu, B, 30);
-    bool keep = owned && B > Bc && Bc < n - 1;
-    unsigned bal = __ballot_sync(0xffffffffu, keep);
-    unsigned prevbal = __ballot_sync(0xffffffffu, owned);
-    const bool look = __shfl_sync(0xffffffffu, (int)valid, 31) != 0;  // the lookahead element exists
-#pragma unroll 1
-    for (int inner = 0; inner < MAX_INNER && bal != prevbal; ++inner) {  // something was dropped: relink, re-test (uniform)
-        prevbal = bal;
-        const unsigned link = bal | (look ? 0x80000000u : 0u);
-        const unsigned right = (lane < 31) ? (link >> (lane + 1)) : 0u;
-        const unsigned left = bal & ((1u << lane) - 1u);
-        const int nl = right ? lane + __ffs(right) : 0;     // nearest kept lane to the right (or the lookahead)
-        const int pl = left ? 31 - __clz(left) : 0;         // nearest kept lane to the left
-        const unsigned vr = __shfl_sync(0xffffffffu, v, nl);
-        const int xr = (int)(vr & 0xffffu), gr = (int)(vr >> 16) - Y, Hr = xr * xr + gr * gr;
-        const int Bn = right ? breakpoint_gap(Hr - H, xr - x, n, lut) : n - 1;  // against my nearest kept right neighbour
-        const int Bl = __shfl_sync(0xffffffffu, Bn, pl);  // B(nearest kept left neighbour, me): just computed against me
-        B = min(B, Bn);                 // both are bounds by real candidates to my right
-        if (left) Bc = max(Bc, Bl);     // likewise on the left (without a kept left lane the Jacobi bound stays)
-        keep = keep && B > Bc && Bc < n - 1;
-        bal = __ballot_sync(0xffffffffu, keep);
+// ---- cp.async (LDGSTS): global -> shared without a register round trip, completion by commit groups
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int pending) {   // warp-uniform
+    switch (pending) {
+        case 0: cp_async_wait<0>(); break;
+        case 1: cp_async_wait<1>(); break;
+        case 2: cp_async_wait<2>(); break;
+        default: cp_async_wait<3>(); break;
     }
-    return keep;
 }
-
-#ifndef BAND_SITETAB
-#define BAND_SITETAB 0   // > 0 (slots, e.g. 768): per-band shared-memory table that sums a site's runs over the band's rows,
-#endif                   // so that the site-id lookup and the three global fp64 REDs happen once per site per band instead
-                         // of once per run (~6x fewer).  PREPARED IN ROUND 1 WITHOUT GPU TIME LEFT: compiles, never run.
-
-#if BAND_SITETAB > 0
-#define SITETAB_EMPTY 0xffffffffu   // no packed site has the top bit set (row < 32768)
-struct SiteTab {
-    unsigned *key;     // packed site (x | c << 16) or SITETAB_EMPTY
-    double *sum;       // 3 doubles per slot: W, X, Y*W
-};
-__device__ __forceinline__ unsigned sitetab_slot(unsigned v) {
-    return (unsigned)(((unsigned long long)(v * 2654435761u) * (unsigned)BAND_SITETAB) >> 32);   // multiplicative hash -> [0, slots)
-}
-// Adds a run's sums to its site's slot; false if no slot was found within a few probes (the caller then updates the
-// global accumulators directly, as the table-less kernel does).
-__device__ __forceinline__ bool sitetab_add(const SiteTab &T, unsigned v, double W, double X, double YW) {
-    unsigned h = sitetab_slot(v);
-#pragma unroll 1
-    for (int probe = 0; probe < 8; ++probe) {
-        const unsigned k = atomicCAS(&T.key[h], SITETAB_EMPTY, v);
-        if (k == SITETAB_EMPTY || k == v) {
-            atomicAdd(&T.sum[3 * h], W);
-            atomicAdd(&T.sum[3 * h + 1], X);
-            atomicAdd(&T.sum[3 * h + 2], YW);
-            return true;
-        }
-        h = (h + 1 == (unsigned)BAND_SITETAB) ? 0u : h + 1;
-    }
-    return false;
-}
-#endif
 
 // Measurement code is compiled in only with -DSRM_MEASURE (tools/prof_band.py, tools/ablate_band.py build that variant):
 // per-phase clock64 counters (dbg & 1) and the ablation switches of the accumulation (dbg & 2: no atomics, dbg & 4:
@@ -304,62 +234,28 @@ __device__ __forceinline__ bool sitetab_add(const SiteTab &T, unsigned v, double
 // [6] warps that took the staging-overflow fallback of Phase A
 #define SRM_STAT_ADD(slot, v) do { if ((dbg & 1) && lane == 0) atomicAdd(&ctl->dbg[slot], (int)(v)); } while (0)
 
-template <int RPW, int C, int GS0, int GS1>
+template <int RPW, int C>
 __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
                                                   const short *__restrict__ dn, int n, int row0, int CL,
                                                   int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                   const int *__restrict__ idmap, double *__restrict__ acc, int Kcap,
-                                                  SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
-                                                  int dbg, int nbands) {
+                                                  SrmCtl *ctl, int flags, int dbg) {
     constexpr int R = BAND_NW * RPW;
     static_assert(R <= 16, "in-band bits are packed in 16 bits");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wcnt[BAND_NW];
-    if (respect_stop && ctl->stop) return;
+    if ((flags & SRM_BF_STOP) && ctl->stop) return;
+    const bool accumulate = flags & SRM_BF_ACC, want_energy = flags & SRM_BF_ENERGY;
 
     uint2 *L = reinterpret_cast<uint2 *>(smem_raw);                       // band list: {x | inband << 16, U | D << 16}
     unsigned char *masks = reinterpret_cast<unsigned char *>(L + CL);      // live mask per 8-column block
     unsigned *buf0 = reinterpret_cast<unsigned *>(masks + ((n / 8 + 15) & ~15));  // per-warp element buffers
-    const unsigned *lut = nullptr;
-#if BAND_LUT > 0
-    {   // reciprocal table behind the element buffers; entry 0 is never used (neighbours are at least one column apart)
-        unsigned *lw = buf0 + (size_t)BAND_NW * C;
-        for (int g = threadIdx.x; g < BAND_LUT; g += BAND_NT) lw[g] = g ? (unsigned)(0x100000000ull / (unsigned long long)(2 * g)) + 1u : 0u;
-        lut = lw;   // published by the __syncthreads() that ends Phase A
-    }
-#endif
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-#if BAND_SITETAB > 0
-    SiteTab tab;
-    {   // behind the element buffers and the reciprocal table; 8-byte aligned (all sizes before it are multiples of 16)
-        unsigned char *tb = reinterpret_cast<unsigned char *>(buf0 + (size_t)BAND_NW * C + BAND_LUT);
-        tab.sum = reinterpret_cast<double *>(tb);
-        tab.key = reinterpret_cast<unsigned *>(tb + (size_t)BAND_SITETAB * 24);
-    }
-#endif
     double e_loc = 0;
-#if BAND_PERSIST
-    // Persistent form: the grid holds as many CTAs as are resident at once and every CTA takes bands from a ticket
-    // until none is left, so an SM keeps its full complement of CTAs until the very end (no partial second wave).
-    __shared__ int s_band;
-    for (;;) {
-        __syncthreads();   // every warp is done with the previous band's shared memory
-        if (t == 0) s_band = atomicAdd(&ctl->band_ticket, 1);
-        __syncthreads();
-        const int bi = s_band;
-        if (bi >= nbands) break;
-#else
-    {
-        const int bi = blockIdx.x;
-        (void)nbands;
-#endif
+    const int bi = blockIdx.x;
     const int rb = bi * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
-#if BAND_SITETAB > 0
-    if (accumulate)   // cleared here, first used after the two barriers of Phase A
-        for (int q = t; q < BAND_SITETAB; q += BAND_NT) { tab.key[q] = SITETAB_EMPTY; tab.sum[3 * q] = 0; tab.sum[3 * q + 1] = 0; tab.sum[3 * q + 2] = 0; }
-#endif
     const size_t wrow = (size_t)j * n;
     const int nb = n >> 3;
     const int bw0 = (w * nb) / BAND_NW, bw1 = ((w + 1) * nb) / BAND_NW;
@@ -414,11 +310,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     if ((dbg & 1) && t == 0) { atomicMax(&ctl->dbg[0], mb); atomicAdd(&ctl->dbg[1], mb); atomicAdd(&ctl->dbg[2], 1); }
     if (mb > CL) {  // band list does not fit: every row of the band goes to the robust path
         if (t < R) ovf_rows[atomicAdd(&ctl->ovf, 1)] = rb + t;
-#if BAND_PERSIST
-        continue;
-#else
         return;
-#endif
     }
     // Every warp assembles its own section [wbase, wbase + mycount) of the band list, so the choice between the two
     // forms below is warp-local (`staged` is warp-uniform): no flag is shared between warps.
@@ -472,8 +364,8 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 int x0 = 0, H0 = 0, x1 = 0, H1 = 0;
                 load_cand(L, min(ea, mb - 1), Y0, k, Y, v0, x0, H0);  // clamped index: no branch, result unused if !va
                 load_cand(L, min(eb, mb - 1), Y0, k, Y, v1, x1, H1);
-                const bool ka = chunk_round<GS0>(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0, lut);
-                const bool kb = chunk_round<GS0>(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0, lut);
+                const bool ka = round_step(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0).keep;
+                const bool kb = round_step(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0).keep;
                 const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
                 if (ka) buf[m + __popc(ba & lt)] = v0;
                 m += __popc(ba);
@@ -502,7 +394,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
 #pragma unroll
                     for (int q = 0; q < BAND_NCH; ++q) {
                         const int e = base + 31 * q + lane;
-                        kk[q] = chunk_round<GS1>(e < m, e + 1 < m, vv[q], xs[q], Hs[q], Y, lane, n, carryB, lut);
+                        kk[q] = round_step(e < m, e + 1 < m, vv[q], xs[q], Hs[q], Y, lane, n, carryB).keep;
                     }
 #pragma unroll
                     for (int q = 0; q < BAND_NCH; ++q) bal[q] = __ballot_sync(0xffffffffu, kk[q]);
@@ -524,116 +416,108 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             if (pos >= mb) break;
             if (m + 62 > C) { overflow = true; break; }  // the envelope itself does not fit
         }
+        // the accumulation ring needs one stage of free space behind the runs
+        const int m4 = (m + 3) & ~3;
+        if (accumulate && (C - m4) * 4 < BAND_STAGE_BYTES) overflow = true;
         if (overflow) {
             if (lane == 0) ovf_rows[atomicAdd(&ctl->ovf, 1)] = r;
             continue;
         }
-        // output pass: runs -> global run-length row, and (accumulate mode) fp64 prefix differences -> site sums
-        int2 *out = rle + (size_t)r * n;
-        const double2 *p2 = P2 + srm_pfx_row(r, n);   // tiled layout: element x at [x * SRM_PFX_TILE]
-        const double *pxx = PXX + srm_pfx_row(r, n);
-        int carryB = -1;
-        double2 carryP = make_double2(0, 0);
-        double carryXX = 0;
-        for (int base = 0; base < m; base += 62) {
-            int ee[2] = {base + lane, base + 31 + lane};
-            unsigned vv[2];
-            int xx[2], cc[2], HH[2];
-            RoundStep st[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const bool valid = ee[q] < m;
-                vv[q] = valid ? buf[ee[q]] : 0u;
-                xx[q] = (int)(vv[q] & 0xffffu); cc[q] = (int)(vv[q] >> 16);
-                const int g = cc[q] - Y;
-                HH[q] = xx[q] * xx[q] + g * g;
-                st[q] = round_step(valid, ee[q] + 1 < m, vv[q], xx[q], HH[q], Y, lane, n, carryB, lut);
-                if (st[q].owned) out[ee[q]] = make_int2((int)vv[q], st[q].Bc + 1);
-            }
-            if (accumulate) {
-                double2 pb[2];
-                double xb[2];
-                int id[2];
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {  // all loads of both chunks first
-                    pb[q] = (st[q].owned && !ABL(8)) ? p2[(size_t)st[q].B * SRM_PFX_TILE] : make_double2(1, 1);
-                    xb[q] = (st[q].owned && want_energy) ? pxx[(size_t)st[q].B * SRM_PFX_TILE] : 0;
-#if BAND_SITETAB > 0
-                    id[q] = -1;   // looked up only by the runs that find no table slot
-#else
-                    id[q] = st[q].owned ? (ABL(4) ? (ee[q] + 37 * r) % Kcap : idmap[(size_t)cc[q] * n + xx[q]]) : 0;
-#endif
-                }
+        if (lane == 0) rle_cnt[r] = m;
+        if (flags & SRM_BF_RLE) {
+            // runs -> global run-length row (final labelling and the stepwise API; nothing in the loop reads it)
+            int2 *out = rle + (size_t)r * n;
+            int carryB = -1;
+            for (int base = 0; base < m; base += 62) {
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
-                    double2 pa;
-                    pa.x = __shfl_up_sync(0xffffffffu, pb[q].x, 1);
-                    pa.y = __shfl_up_sync(0xffffffffu, pb[q].y, 1);
-                    double xa = __shfl_up_sync(0xffffffffu, xb[q], 1);
-                    if (lane == 0) { pa = carryP; xa = carryXX; }
-                    carryP.x = __shfl_sync(0xffffffffu, pb[q].x, 30);
-                    carryP.y = __shfl_sync(0xffffffffu, pb[q].y, 30);
-                    carryXX = __shfl_sync(0xffffffffu, xb[q], 30);
-                    if (st[q].owned) {
-                        const double W = pb[q].x - pa.x, X = pb[q].y - pa.y;
-#if BAND_SITETAB > 0
-                        if (!sitetab_add(tab, vv[q], W, X, (double)Y * W)) id[q] = idmap[(size_t)cc[q] * n + xx[q]];
-                        double *a = acc + 4 * (size_t)max(id[q], 0);
-                        if (id[q] >= 0) {
-#else
-                        double *a = acc + 4 * (size_t)id[q];
-                        if (!ABL(2)) {
-#endif
-                            atomicAdd(a, W);
-                            atomicAdd(a + 1, X);
-                            atomicAdd(a + 2, (double)Y * W);
-                            reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id[q]] = 1;
-                        }
-#ifdef SRM_MEASURE
-                        else if (W == -1.5) a[3] = X;   // keeps the loads alive when the atomics are ablated
-#endif
-                        if (want_energy) e_loc += (xb[q] - xa) - 2.0 * (double)xx[q] * X + (double)(HH[q]) * W;
-                    }
+                    const int e = base + 31 * q + lane;
+                    const bool valid = e < m;
+                    const unsigned v = valid ? buf[e] : 0u;
+                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+                    const RoundStep st = round_step(valid, e + 1 < m, v, x, x * x + g * g, Y, lane, n, carryB);
+                    if (st.owned) out[e] = make_int2((int)v, st.Bc + 1);
                 }
             }
         }
-        if (lane == 0) rle_cnt[r] = m;
+        if (accumulate) {
+            // Per-site sums of the row's runs: run e = (B(e-1), B(e)] contributes the fp64 prefix differences of d and
+            // x*d (and x^2*d for the energy) to its site.  The prefix entries at the run ends and the site ids are
+            // fetched by cp.async into a ring of 32-run stages behind the runs in this warp's buffer.
+            unsigned char *ring = reinterpret_cast<unsigned char *>(buf + m4);
+            const int nst = min(BAND_NST, ((C - m4) * 4) / BAND_STAGE_BYTES);   // >= 1 (checked above)
+            const int nbat = (m + 31) >> 5;
+            const double2 *p2 = P2 + srm_pfx_row(r, n);   // tiled layout: element x at [x * SRM_PFX_TILE]
+            const double *pxx = PXX + srm_pfx_row(r, n);
+            unsigned char *touched = reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4);
+            auto issue = [&](int b) {
+                unsigned char *st = ring + (b % nst) * BAND_STAGE_BYTES;
+                const int e = 32 * b + lane;
+                if (e < m) {
+                    const unsigned v = buf[e];
+                    const int x = (int)(v & 0xffffu), c = (int)(v >> 16), g = c - Y;
+                    int B = n - 1;
+                    if (e + 1 < m) {
+                        const unsigned vn = buf[e + 1];
+                        const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y;
+                        B = breakpoint(xn * xn + gn * gn - (x * x + g * g), 2 * (xn - x), n);
+                    }
+                    if (!ABL(8)) cp_async16(st + 16 * lane, p2 + (size_t)B * SRM_PFX_TILE);
+                    if (want_energy) cp_async8(st + 512 + 8 * lane, pxx + (size_t)B * SRM_PFX_TILE);
+                    if (!ABL(4)) cp_async4(st + 768 + 4 * lane, idmap + (size_t)c * n + x);
+                }
+                cp_async_commit();   // one group per batch, empty ones included: uniform group accounting
+            };
+            for (int b = 0; b < nst; ++b) issue(b);
+            double2 carryP = make_double2(0, 0);
+            double carryXX = 0;
+            for (int b = 0; b < nbat; ++b) {
+                cp_async_wait_pending(nst - 1);
+                __syncwarp();   // the stage holds every lane's entries
+                const unsigned char *st = ring + (b % nst) * BAND_STAGE_BYTES;
+                const int e = 32 * b + lane;
+                const bool valid = e < m;
+                const double2 *sp = reinterpret_cast<const double2 *>(st);
+                const double *sx = reinterpret_cast<const double *>(st + 512);
+                const double2 pb = (valid && !ABL(8)) ? sp[lane] : make_double2(1, 1);
+                const double2 pa = lane ? ((valid && !ABL(8)) ? sp[lane - 1] : make_double2(1, 1)) : carryP;
+                const double xb = (valid && want_energy) ? sx[lane] : 0, xa = lane ? ((valid && want_energy) ? sx[lane - 1] : 0) : carryXX;
+                int id = valid ? (ABL(4) ? (e + 37 * r) % Kcap : reinterpret_cast<const int *>(st + 768)[lane]) : 0;
+                carryP = sp[31]; carryXX = want_energy ? sx[31] : 0;   // broadcast reads; only full batches have a successor
+                if (valid) {
+                    const unsigned v = buf[e];
+                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+                    const double W = pb.x - pa.x, X = pb.y - pa.y;
+                    double *a = acc + 4 * (size_t)id;
+                    if (!ABL(2)) {
+                        atomicAdd(a, W);
+                        atomicAdd(a + 1, X);
+                        atomicAdd(a + 2, (double)Y * W);
+                        if (flags & SRM_BF_TOUCH) touched[id] = 1;
+                    }
+#ifdef SRM_MEASURE
+                    else if (W == -1.5) a[3] = X;   // keeps the loads alive when the atomics are ablated
+#endif
+                    if (want_energy) e_loc += (xb - xa) - 2.0 * (double)x * X + (double)(x * x + g * g) * W;
+                }
+                __syncwarp();   // every lane has read the stage before it is refilled
+                if (b + nst < nbat) issue(b + nst); else cp_async_commit();
+            }
+            cp_async_wait<0>();
+        }
         __syncwarp();
         PROF_ADD(5);   // output + accumulate
         PROF_CNT(14, m);
     }
-#if BAND_SITETAB > 0
-    if (accumulate) {   // every warp's rows are in the table: one id lookup and one set of global REDs per site of the band
-        __syncthreads();
-        for (int q = t; q < BAND_SITETAB; q += BAND_NT) {
-            const unsigned v = tab.key[q];
-            if (v == SITETAB_EMPTY) continue;
-            const int id = idmap[(size_t)(v >> 16) * n + (v & 0xffffu)];
-            double *a = acc + 4 * (size_t)id;
-            atomicAdd(a, tab.sum[3 * q]);
-            atomicAdd(a + 1, tab.sum[3 * q + 1]);
-            atomicAdd(a + 2, tab.sum[3 * q + 2]);
-            reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id] = 1;
-        }
-    }
-#endif
-    }   // band (loop in the persistent form)
     if (accumulate && want_energy) {
         e_loc = warp_sum(e_loc);
         if (lane == 0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
     }
 }
 
-#ifndef BAND_GS0
-#define BAND_GS0 0   // in-chunk Gauss-Seidel sweeps allowed in round 0 (band list)
-#endif
-#ifndef BAND_GS1
-#define BAND_GS1 0   // ... and in the later rounds.  Measured on a B200 (8192^2, C3): sweeps cut the passes per row
-                      // from 8.3 to 2.6-3.2 but add serial latency; (0,0) 253 us, (0,8) 257, (1,4) 253, (2,4) 278, (3,8) 295.
-#endif
-
-// Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62.  Rows of an n-wide grid with the
-// BASELINE site densities have ~n/26 runs (316 at 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
+// Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62 (and, when accumulating, one 896-byte
+// stage of the prefix ring).  Rows of an n-wide grid with the BASELINE site densities have ~n/26 runs (316 at
+// 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
 static int band_bufcap(int n) { return n <= 8192 ? BAND_C8K : n <= 16384 ? 1280 : 1792; }
 
 static int band_cap(int n) {
@@ -651,13 +535,12 @@ static int band_cap(int n) {
 }
 
 static size_t band_smem(int n, int CL) {
-    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4 + (size_t)BAND_LUT * 4 +
-           (size_t)BAND_SITETAB * 28;   // site table: 3 doubles + key per slot
+    return (size_t)CL * 8 + (size_t)((n / 8 + 15) & ~15) + (size_t)BAND_NW * band_bufcap(n) * 4;
 }
 
 template <int RPW, int C>
 static cudaError_t band_setup_one(int smem) {
-    return cudaFuncSetAttribute(k_band<RPW, C, BAND_GS0, BAND_GS1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    return cudaFuncSetAttribute(k_band<RPW, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 cudaError_t srm_band_setup(int n) {
@@ -691,33 +574,19 @@ static int band_rpw(int nrows) {
 template <int RPW, int C>
 static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, const short *up, const short *dn, SrmGrid g,
                             int CL, int2 *rle, int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX,
-                            const int *idmap, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
-                            int respect_stop, int dbg) {
+                            const int *idmap, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int nbands = g.nrows() / (BAND_NW * RPW);
-    int grid = nbands;
-#if BAND_PERSIST
-    {
-        static int per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}}, sms = 0;   // resident CTAs per SM of this instantiation
-        const int ci = C == BAND_C8K ? 0 : C == 1280 ? 1 : 2;
-        if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-        if (!per_sm[RPW - 1][ci])
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[RPW - 1][ci], k_band<RPW, C, BAND_GS0, BAND_GS1>, BAND_NT, smem);
-        grid = min(nbands, max(1, per_sm[RPW - 1][ci]) * max(1, sms));
-    }
-#endif
-    SRM_COUNT(), k_band<RPW, C, BAND_GS0, BAND_GS1><<<grid, BAND_NT, smem, st>>>(
-        bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy,
-        respect_stop, dbg, nbands);
+    SRM_COUNT(), k_band<RPW, C><<<nbands, BAND_NT, smem, st>>>(bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX,
+                                                              idmap, acc, Kcap, ctl, flags, dbg);
 }
 
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                             int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
-                            double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
-                            int dbg) {
+                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int CL = band_cap(g.n);
     const size_t smem = band_smem(g.n, CL);
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
-#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop, dbg
+#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, flags, dbg
     if (C == BAND_C8K) { if (rpw == 1) band_launch_one<1, BAND_C8K>(BAND_ARGS); else band_launch_one<2, BAND_C8K>(BAND_ARGS); }
     else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
     else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }

@@ -101,10 +101,17 @@ void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, s
                       int respect_stop, int row0, int row1, const int *edge);
 // fused fast path (srm_band.cu)
 cudaError_t srm_band_setup(int n);
+// flags of the band kernel
+enum {
+    SRM_BF_ACC = 1,      // accumulate the per-site sums (fused centroid pass)
+    SRM_BF_ENERGY = 2,   // ... and the CVT energy
+    SRM_BF_STOP = 4,     // return at once if the device-side stop flag is set
+    SRM_BF_RLE = 8,      // write the run-length rows (final labelling, stepwise API; the loop does not need them)
+    SRM_BF_TOUCH = 16    // mark the sites this rank contributed to (read by the peer-memory all-reduce)
+};
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                             int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
-                            double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy, int respect_stop,
-                            int dbg = 0);
+                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg = 0);
 // robust path, driven by a row list (rows == nullptr: every row of the band)
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                            int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,

@@ -14,6 +14,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the ablation switches exist only in the -DSRM_MEASURE build: tools/build_variant.sh measure "-DSRM_MEASURE"
+os.environ.setdefault("SRM_LIB", os.path.join(ROOT, "build", "variants", "libsrm_measure.so"))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench                      # noqa: E402
 import surface_remesher_b200 as S  # noqa: E402
