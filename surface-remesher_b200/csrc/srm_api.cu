@@ -39,6 +39,13 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 long long g_srm_launches = 0;
+bool srm_pdl_enabled() {
+#ifdef SRM_NO_PDL
+    return false;
+#endif
+    static const bool on = []() { const char *e = getenv("SRM_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 extern "C" long long srm_launch_count(void) { return __sync_fetch_and_add(&g_srm_launches, 0ll); }
 extern "C" const char *srm_last_error(void) { return g_err; }
 extern "C" int srm_version(void) { return 100; }
@@ -94,16 +101,18 @@ struct srm_ctx {
     double *acc = nullptr;
     int *newpos = nullptr, *blockcnt = nullptr, *blockoff = nullptr;
     size_t blockcap = 0;
-    // labelling state
-    uint32_t *bits = nullptr;
-    short *up = nullptr, *dn = nullptr;
+    // labelling state.  bits / up / dn hold the context's own word rows only; the base pointers are shifted so that the
+    // kernels index them with absolute rows: [(y >> 5) * n + x].  bits, edge and hash alternate by iteration parity.
+    uint32_t *bits_alloc[2] = {nullptr, nullptr}, *bits[2] = {nullptr, nullptr};
+    short *up_alloc = nullptr, *dn_alloc = nullptr, *up = nullptr, *dn = nullptr;
+    size_t band_words = 0;
     int2 *rle = nullptr;
-    int *rle_cnt = nullptr, *idmap = nullptr, *claim = nullptr, *labels = nullptr, *scratch_map = nullptr;
+    int *rle_cnt = nullptr, *labels = nullptr, *scratch_map = nullptr;
     int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
-    int *edge = nullptr;       // row bands: per column, nearest site row above / below the band (2n ints)
+    int *edge[2] = {nullptr, nullptr};   // row bands: per column, nearest site row above / below the band (2n ints)
+    SrmHash hash[2];           // pixel -> site id (and the dedupe claims of the update)
     int dbg_stats = 0;
     bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
-    bool claim_dirty = false;  // an update has written dedupe claims that the next labelling has not reset yet
     SrmCtl *ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
@@ -134,10 +143,20 @@ static int alloc_sites(srm_ctx *c, int K) {
         return fail(SRM_ERR_STATE, "site set of %d entries exceeds the capacity %d the row-band collective was set up "
                                    "with: destroy the band contexts and reconnect", K, c->Kcap);
     for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
+    for (int i = 0; i < 2; ++i) if (c->hash[i].b) { cudaFree(c->hash[i].b); c->hash[i].b = nullptr; }
     if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
     if (c->newpos) { cudaFree(c->newpos); c->newpos = nullptr; }
     c->Kcap = K;
     size_t k1 = (size_t)(K > 0 ? K : 1);
+    {   // hash tables: two-slot buckets, buckets = power of two >= 2 K (slot load <= 0.25, 16 bytes per bucket)
+        int lg = 10;
+        while ((1ull << lg) < 2 * k1 && lg < 30) ++lg;
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaMalloc(&c->hash[i].b, sizeof(uint4) << lg));
+            c->hash[i].mask = (1u << lg) - 1u;
+            c->hash[i].shift = 32 - lg;
+        }
+    }
     CK(cudaMalloc(&c->sites[0], k1 * sizeof(int)));
     CK(cudaMalloc(&c->sites[1], k1 * sizeof(int)));
     CK(cudaMalloc(&c->newpos, k1 * sizeof(int)));
@@ -152,11 +171,6 @@ static int alloc_sites(srm_ctx *c, int K) {
 }
 
 static int reset_ctl(srm_ctx *c, int K) {
-    if (c->claim_dirty) {   // an update wrote claims that no labelling has reset since (k_bits resets them at the live
-        srm_launch_fill_int(c->stream, c->claim, c->N, INT_MAX);   // sites): a new site set must not see them
-        CK(cudaGetLastError());
-        c->claim_dirty = false;
-    }
     SrmCtl h;
     memset(&h, 0, sizeof(h));
     h.K = K; h.nlive = K; h.omega = 2.0f; h.lastE = 1e18f; h.E = 0.0f;  // gcvt.cu:1105-1108
@@ -167,6 +181,26 @@ static int reset_ctl(srm_ctx *c, int K) {
     c->it_host = 0;
     c->stopped = false;
     c->labelled = false;
+    return SRM_OK;
+}
+
+static bool is_band(const srm_ctx *c) { return c->g.row0 > 0 || c->g.row1 < c->g.n; }
+
+// Buffer sets of iteration `it`: cur = it & 1 is read by the labelling, next is cleared by the carry kernel and
+// filled by the update.
+static SrmStep step_of(srm_ctx *c, int it) {
+    const int cur = it & 1, nxt = cur ^ 1;
+    SrmStep s;
+    s.bits = c->bits[cur]; s.edge = is_band(c) ? c->edge[cur] : nullptr; s.hash = c->hash[cur];
+    s.bits_next = c->bits[nxt]; s.edge_next = is_band(c) ? c->edge[nxt] : nullptr; s.hash_next = c->hash[nxt];
+    return s;
+}
+
+// Bitmap, band edges and hash of the buffer set `parity` from the site list sites[parity] (ctl->K entries).
+static int init_step_buffers(srm_ctx *c, int parity) {
+    srm_launch_init_sites(c->stream, c->sites[parity], c->ctl, c->Kcap, c->g.n, c->bits[parity], c->band_words,
+                          is_band(c) ? c->edge[parity] : nullptr, c->hash[parity], c->g.row0, c->g.row1);
+    CK(cudaGetLastError());
     return SRM_OK;
 }
 
@@ -203,15 +237,20 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->mask, c->N));
     CKD(cudaMalloc(&c->P2, NB * sizeof(double2)));
     CKD(cudaMalloc(&c->PXX, NB * sizeof(double)));
-    CKD(cudaMalloc(&c->bits, NW * sizeof(uint32_t)));
-    CKD(cudaMalloc(&c->up, NW * sizeof(short)));
-    CKD(cudaMalloc(&c->dn, NW * sizeof(short)));
+    (void)NW;
+    c->band_words = (size_t)(c->g.nrows() >> 5) * n;
+    const size_t woff = (size_t)(row0 >> 5) * n;   // kernels index with absolute word rows
+    for (int i = 0; i < 2; ++i) {
+        CKD(cudaMalloc(&c->bits_alloc[i], c->band_words * sizeof(uint32_t)));
+        c->bits[i] = c->bits_alloc[i] - woff;
+        CKD(cudaMalloc(&c->edge[i], 2 * (size_t)n * sizeof(int)));
+    }
+    CKD(cudaMalloc(&c->up_alloc, c->band_words * sizeof(short)));
+    CKD(cudaMalloc(&c->dn_alloc, c->band_words * sizeof(short)));
+    c->up = c->up_alloc - woff; c->dn = c->dn_alloc - woff;
     CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
-    CKD(cudaMalloc(&c->edge, 2 * (size_t)n * sizeof(int)));
-    CKD(cudaMalloc(&c->idmap, c->N * sizeof(int)));
-    CKD(cudaMalloc(&c->claim, c->N * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
     CKD(cudaMalloc(&c->flags, 64 * sizeof(int)));
     CKD(cudaMemsetAsync(c->flags, 0, 64 * sizeof(int), c->stream));
@@ -220,8 +259,6 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->blockoff, c->blockcap * sizeof(int)));
     CKD(cudaMemsetAsync(c->ctl, 0, sizeof(SrmCtl), c->stream));
     CKD(srm_label_setup(n));
-    srm_launch_fill_int(c->stream, c->claim, c->N, INT_MAX);
-    CKD(cudaGetLastError());
     CKD(cudaStreamSynchronize(c->stream));
 #undef CKD
     *out = c;
@@ -238,8 +275,8 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
     if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
     void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
-                    c->blockoff, c->bits, c->up, c->dn, c->rle, c->rle_cnt, c->ovf_rows, c->edge, c->idmap, c->claim, c->labels,
-                    c->scratch_map, c->ctl};
+                    c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->rle_cnt, c->ovf_rows,
+                    c->edge[0], c->edge[1], c->hash[0].b, c->hash[1].b, c->labels, c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -430,6 +467,8 @@ extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device
     CK(cudaGetLastError());
     rc = reset_ctl(c, K);
     if (rc) return rc;
+    rc = init_step_buffers(c, 0);
+    if (rc) return rc;
     c->has_sites = true;
     return SRM_OK;
 }
@@ -449,6 +488,8 @@ extern "C" int srm_set_sites(srm_ctx *c, const int *packed_xy, int num, int on_d
         CK(cudaMemcpyAsync(c->sites[0], packed_xy, (size_t)num * sizeof(int),
                            on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
     rc = reset_ctl(c, num);
+    if (rc) return rc;
+    rc = init_step_buffers(c, 0);
     if (rc) return rc;
     c->has_sites = true;
     return SRM_OK;
@@ -596,22 +637,20 @@ static int band_flags(srm_ctx *c, int respect_stop, int accumulate, int want_ene
 
 // write_rle: the run-length rows are needed by srm_get_labels / srm_accumulate after this labelling (not inside the loop)
 static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy, int write_rle = 1) {
-    const int buf = it & 1;
     double *acc = cur_acc(c, it);
-    srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, respect_stop, c->g.row0, c->g.row1, c->edge);
-    srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1, c->edge);
+    const SrmStep s = step_of(c, it);
+    srm_launch_carry(c->stream, s, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1);
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
-        CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                           c->idmap, acc, c->Kcap, c->ctl, band_flags(c, respect_stop, accumulate, want_energy, write_rle),
+        CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+                           s.hash, acc, c->Kcap, c->ctl, band_flags(c, respect_stop, accumulate, want_energy, write_rle),
                            c->dbg_stats));
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
-    CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
+    CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, s.hash,
                       acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
     if (accumulate) srm_launch_signal(c->stream, c->ctl, peers_of(c, it), respect_stop);
-    c->claim_dirty = false;   // k_bits reset the claims at every live site
     return SRM_OK;
 }
 
@@ -649,8 +688,8 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     if (rc) return rc;
     if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
     CK(cudaSetDevice(c->device));
-    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->idmap, c->g, cur_acc(c, c->it_host), c->Kcap, nullptr,
-                   nullptr, c->ctl, want_energy, 0);
+    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->hash[c->it_host & 1], c->g, cur_acc(c, c->it_host), c->Kcap,
+                   nullptr, nullptr, c->ctl, want_energy, 0);
     srm_launch_signal(c->stream, c->ctl, peers_of(c, c->it_host), 0);
     CK(cudaGetLastError());
     return SRM_OK;
@@ -675,10 +714,10 @@ extern "C" int srm_update(srm_ctx *c) {
     //  srm_acc_buffer hands out the sums, so nothing to check here)
     const int buf = current_buffer(c);
     srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
-                      c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, (c->it_host % 10) == 0, 0, 0, peers_of(c, c->it_host));
+                      c->g, c->ctl, c->Kcap, c->newpos, step_of(c, c->it_host), (c->it_host % 10) == 0, 0, 0,
+                      peers_of(c, c->it_host));
     CK(cudaGetLastError());
     c->labelled = false;
-    c->claim_dirty = true;
     c->it_host += 1;
     return SRM_OK;
 }
@@ -698,13 +737,12 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
         rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
         if (rc) return rc;
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
+                          c->has_mask ? c->mask : nullptr, c->g, c->ctl, c->Kcap, c->newpos, step_of(c, it), want_energy,
                           stop_rule, 1, peers_of(c, it));
     }
     CK(cudaGetLastError());
     c->it_host = it;
     c->labelled = false;
-    c->claim_dirty = true;
     if (stop_rule) {  // the device may have stopped early: resynchronise the host mirror
         SrmCtl h;
         rc = fetch_ctl(c, &h);
@@ -733,18 +771,18 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         cudaEvent_t *e = &ev[(size_t)i * 6];
         CK(cudaEventRecord(e[0], c->stream));
         double *acc = cur_acc(c, it);
-        srm_launch_bits(c->stream, c->sites[buf], c->ctl, c->Kcap, c->g.n, c->bits, c->idmap, c->claim, 1, c->g.row0, c->g.row1, c->edge);
-        srm_launch_carry(c->stream, c->bits, c->g.n, c->up, c->dn, c->ctl, 1, c->g.row0, c->g.row1, c->edge);
+        const SrmStep s = step_of(c, it);
+        srm_launch_carry(c->stream, s, c->g.n, c->up, c->dn, c->ctl, 1, c->g.row0, c->g.row1);
         CK(cudaEventRecord(e[1], c->stream));
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {
-            CK(srm_launch_band(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
-                               c->idmap, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats));
+            CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+                               s.hash, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats));
             rows = c->ovf_rows;
             count = &c->ctl->ovf;
         }
         CK(cudaEventRecord(e[2], c->stream));
-        CK(srm_launch_row(c->stream, c->bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, c->idmap,
+        CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, s.hash,
                           acc, c->Kcap, c->ctl, 1, want_energy, 1));
         CK(cudaEventRecord(e[3], c->stream));
         srm_launch_signal(c->stream, c->ctl, peers_of(c, it), 1);
@@ -752,7 +790,7 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         if (rc) return rc;
         CK(cudaEventRecord(e[4], c->stream));
         srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g.n, c->ctl, c->Kcap, c->newpos, c->claim, want_energy,
+                          c->has_mask ? c->mask : nullptr, c->g, c->ctl, c->Kcap, c->newpos, s, want_energy,
                           stop_rule, 1, peers_of(c, it));
         CK(cudaEventRecord(e[5], c->stream));
     }
@@ -772,7 +810,6 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
     for (auto &e : ev) cudaEventDestroy(e);
     c->it_host = it;
     c->labelled = false;
-    c->claim_dirty = true;
     SrmCtl h;
     return fetch_ctl(c, &h);
 }
@@ -923,6 +960,7 @@ static int gcvt_multires(srm_ctx *c0, short *voronoi, const float *density, cons
             MR(reset_ctl(f, h.K));
             srm_launch_zoom_sites(f->stream, c->sites[current_buffer(c)], f->sites[h.it & 1], h.K);
             MRC(cudaGetLastError());
+            MR(init_step_buffers(f, h.it & 1));   // the finer level continues the iteration count: parity h.it & 1
             f->has_sites = true;
         }
     }

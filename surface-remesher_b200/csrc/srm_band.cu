@@ -31,7 +31,6 @@
 //
 // Compile-time switches (defaults = the measured best; profiles/r1_kernel_log.md, profiles/r2_kernel_log.md):
 //   BAND_REACH    3   neighbouring 8-column blocks per side used by the band-level pruning (1: band list 1.7x longer)
-//   BAND_NCH      2   chunks in flight in the round loop (3, 4: no effect)
 //   BAND_MINCTA   4   resident CTAs per SM the register allocation aims at; BAND_C8K / BAND_CL8K = buffer and band-list
 //                     capacities for n <= 8192 (5 or 6 CTAs per SM with smaller capacities: no gain / slower)
 //   BAND_NST      4   stages of the accumulation ring (1 = issue, wait, consume: the round-1 behaviour)
@@ -58,7 +57,8 @@
 #ifndef BAND_NST
 #define BAND_NST 4         // stages (of 32 runs) of the accumulation ring
 #endif
-#define BAND_STAGE_BYTES 896   // one stage: 32 x (16 B prefix pair + 8 B x^2 prefix + 4 B site id)
+// one stage of the ring: 32 x (16 B prefix pair + 16 B hash bucket of the run's site [+ 8 B x^2 prefix on energy steps])
+#define BAND_STAGE_BYTES(energy) ((energy) ? 1280 : 1024)
 
 struct Col8 {          // 8 consecutive columns of one band
     int U[8], D[8];    // nearest site row above / below the band (SRM_MARK if none)
@@ -155,10 +155,6 @@ __device__ __forceinline__ int breakpoint(int num, int den, int n) {
     return min(q, n - 1);
 }
 
-#ifndef BAND_NCH
-#define BAND_NCH 2     // 31-element chunks in flight per iteration of the round loop over the element buffer
-#endif
-
 // Candidate of band-list entry i for row Y = Y0 + k: packed x | c << 16 and H = x^2 + (c - Y)^2.
 __device__ __forceinline__ void load_cand(const uint2 *__restrict__ L, int i, int Y0, int k, int Y, unsigned &v, int &x,
                                           int &H) {
@@ -168,6 +164,12 @@ __device__ __forceinline__ void load_cand(const uint2 *__restrict__ L, int i, in
     const int g = c - Y;
     v = (unsigned)x | ((unsigned)c << 16);
     H = x * x + g * g;
+}
+
+__device__ __forceinline__ unsigned load_cand_v(const uint2 *__restrict__ L, int i, int Y0, int k, int Y) {
+    const uint2 e = L[i];
+    const int c = row_candidate((int)(short)(e.y & 0xffffu), (int)e.y >> 16, e.x >> 16, Y0, k, Y);
+    return (e.x & 0xffffu) | ((unsigned)c << 16);
 }
 
 // One step of a dominance round over 31 consecutive elements (lane 31 is a read-only lookahead).
@@ -191,6 +193,37 @@ __device__ __forceinline__ RoundStep round_step(bool valid, bool validn, unsigne
     carryB = __shfl_sync(0xffffffffu, r.B, 30);
     r.keep = r.owned && r.B > r.Bc && r.Bc < n - 1;
     return r;
+}
+
+// The same dominance test WITHOUT the integer division, for the rounds: element e (neighbours p < e < q in the round's
+// input list) can hold a pixel only if the REAL interval (B(p,e), B(e,q)] is non-empty and meets [0, n-1], i.e.
+//     N1/D1 > N0/D0,   N1 >= 0,   N0/D0 < n-1       with N1/D1 = B(e,q), N0/D0 = B(p,e) as exact fractions,
+// compared by cross-multiplication in 64 bits (|N| < 2^31, D < 2^16).  This is necessary for the exact test of
+// round_step (which also asks for an INTEGER in the interval), so every drop is sound, and its fixpoint is the real
+// lower envelope: consecutive breakpoints strictly increasing.  Elements of that envelope whose interval holds no
+// integer ("ghosts", rare: sites are several pixels apart) survive the rounds; they own no pixel, so
+//   * the accumulation adds exact zeros for them (their run is empty: floor(B(g,q)) == floor(B(p,g)), and the floors of
+//     all breakpoints across a chain of ghosts coincide, so the neighbouring runs keep their exact extents), and
+//   * the run-length output removes them with ONE exact pass (their envelope neighbours are their list neighbours).
+// Replaces ~20 instructions incl. four XU-pipe operations per element and round (28 % of the kernel's instructions
+// in the round-2 ncu capture, profiles/r2_ncu_band_summary.md) by ~10 ALU instructions.
+__device__ __forceinline__ bool dom_step(bool valid, bool validn, bool first, unsigned v, int Y, int lane, int n,
+                                         unsigned &carryV) {
+    const unsigned vn = __shfl_down_sync(0xffffffffu, v, 1);
+    unsigned vp = __shfl_up_sync(0xffffffffu, v, 1);
+    if (lane == 0) vp = carryV;
+    carryV = __shfl_sync(0xffffffffu, v, 30);
+    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+    const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y;
+    const int xp = (int)(vp & 0xffffu), gp = (int)(vp >> 16) - Y;
+    const int D1 = xn - x, D0 = x - xp;                         // half denominators
+    const int N1 = D1 * (xn + x) + (gn - g) * (gn + g);         // H_q - H_e
+    const int N0 = D0 * (x + xp) + (g - gp) * (g + gp);         // H_e - H_p
+    const bool hasp = !(first && lane == 0);
+    const bool c1 = !validn || N1 >= 0;
+    const bool c2 = !hasp || N0 < 2 * (n - 1) * D0;
+    const bool c3 = !(validn && hasp) || (long long)N1 * (long long)D0 > (long long)N0 * (long long)D1;
+    return valid && lane < 31 && c1 && c2 && c3;
 }
 
 // ---- cp.async (LDGSTS): global -> shared without a register round trip, completion by commit groups
@@ -239,12 +272,13 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                                                   const short *__restrict__ dn, int n, int row0, int CL,
                                                   int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
-                                                  const int *__restrict__ idmap, double *__restrict__ acc, int Kcap,
+                                                  SrmHash hash, double *__restrict__ acc, int Kcap,
                                                   SrmCtl *ctl, int flags, int dbg) {
     constexpr int R = BAND_NW * RPW;
     static_assert(R <= 16, "in-band bits are packed in 16 bits");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int wcnt[BAND_NW];
+    srm_pdl_enter();
     if ((flags & SRM_BF_STOP) && ctl->stop) return;
     const bool accumulate = flags & SRM_BF_ACC, want_energy = flags & SRM_BF_ENERGY;
 
@@ -353,19 +387,17 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     const unsigned lt = (1u << lane) - 1u;
     for (int rr = 0; rr < RPW; ++rr) {
         const int k = w * RPW + rr, r = rb + k, Y = Y0 + k;
-        int m = 0, pos = 0, carry0 = -1;
+        int m = 0, pos = 0;
+        unsigned carry0 = 0;
         bool overflow = false;
         for (;;) {
             // round 0: candidates of the band list, tested against their list neighbours, appended to buf
             while (pos < mb && m + 62 <= C) {
                 const int ea = pos + lane, eb = pos + 31 + lane;
-                const bool va = ea < mb, vb = eb < mb;
-                unsigned v0 = 0, v1 = 0;
-                int x0 = 0, H0 = 0, x1 = 0, H1 = 0;
-                load_cand(L, min(ea, mb - 1), Y0, k, Y, v0, x0, H0);  // clamped index: no branch, result unused if !va
-                load_cand(L, min(eb, mb - 1), Y0, k, Y, v1, x1, H1);
-                const bool ka = round_step(va, ea + 1 < mb, v0, x0, H0, Y, lane, n, carry0).keep;
-                const bool kb = round_step(vb, eb + 1 < mb, v1, x1, H1, Y, lane, n, carry0).keep;
+                const unsigned v0 = load_cand_v(L, min(ea, mb - 1), Y0, k, Y);   // clamped index: no branch, unused if invalid
+                const unsigned v1 = load_cand_v(L, min(eb, mb - 1), Y0, k, Y);
+                const bool ka = dom_step(ea < mb, ea + 1 < mb, pos == 0, v0, Y, lane, n, carry0);
+                const bool kb = dom_step(eb < mb, eb + 1 < mb, false, v1, Y, lane, n, carry0);
                 const unsigned ba = __ballot_sync(0xffffffffu, ka), bb = __ballot_sync(0xffffffffu, kb);
                 if (ka) buf[m + __popc(ba & lt)] = v0;
                 m += __popc(ba);
@@ -375,32 +407,32 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             }
             __syncwarp();
             PROF_ADD(2); PROF_CNT(10, m); PROF_CNT(11, 1);
-            // rounds over buf until nothing is dropped
+            // rounds over buf until nothing is dropped.  Two independent 31-element chunks per iteration (only the carry
+            // shuffle links them): a warp's step is a chain of dependent shared-memory / shuffle / ballot latencies, and
+            // the second chunk fills it.  Measured alternatives (profiles/r2_kernel_log.md): one chunk per step with
+            // "dirty" flags that skip steps whose elements kept both neighbours (fewer instructions, 165 us against 148:
+            // the chain per step got longer), 3 or 4 chunks (no effect).
             for (;;) {
-                int wp = 0, carryB = -1;
-                for (int base = 0; base < m; base += 31 * BAND_NCH) {
-                    // BAND_NCH independent 31-element chunks per iteration (only the carry shuffle links them)
-                    unsigned vv[BAND_NCH], bal[BAND_NCH];
-                    bool kk[BAND_NCH];
-                    int xs[BAND_NCH], Hs[BAND_NCH];
+                int wp = 0;
+                unsigned carryV = 0;
+                for (int base = 0; base < m; base += 62) {
+                    unsigned vv[2], bal[2];
+                    bool kk[2];
 #pragma unroll
-                    for (int q = 0; q < BAND_NCH; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int e = base + 31 * q + lane;
                         vv[q] = (e < m) ? buf[e] : 0u;
-                        xs[q] = (int)(vv[q] & 0xffffu);
-                        const int g = (int)(vv[q] >> 16) - Y;
-                        Hs[q] = xs[q] * xs[q] + g * g;
                     }
 #pragma unroll
-                    for (int q = 0; q < BAND_NCH; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         const int e = base + 31 * q + lane;
-                        kk[q] = round_step(e < m, e + 1 < m, vv[q], xs[q], Hs[q], Y, lane, n, carryB).keep;
+                        kk[q] = dom_step(e < m, e + 1 < m, base == 0 && q == 0, vv[q], Y, lane, n, carryV);
                     }
 #pragma unroll
-                    for (int q = 0; q < BAND_NCH; ++q) bal[q] = __ballot_sync(0xffffffffu, kk[q]);
+                    for (int q = 0; q < 2; ++q) bal[q] = __ballot_sync(0xffffffffu, kk[q]);
                     __syncwarp();
 #pragma unroll
-                    for (int q = 0; q < BAND_NCH; ++q) {
+                    for (int q = 0; q < 2; ++q) {
                         if (kk[q]) buf[wp + __popc(bal[q] & lt)] = vv[q];
                         wp += __popc(bal[q]);
                     }
@@ -418,10 +450,32 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         }
         // the accumulation ring needs one stage of free space behind the runs
         const int m4 = (m + 3) & ~3;
-        if (accumulate && (C - m4) * 4 < BAND_STAGE_BYTES) overflow = true;
+        const int stage_bytes = BAND_STAGE_BYTES(want_energy);
+        if (accumulate && (C - m4) * 4 < stage_bytes) overflow = true;
         if (overflow) {
             if (lane == 0) ovf_rows[atomicAdd(&ctl->ovf, 1)] = r;
             continue;
+        }
+        if (flags & SRM_BF_RLE) {
+            // exact passes (integer breakpoints): drop the elements whose interval holds no pixel.  One pass removes
+            // them all (see dom_step); the loop runs until a pass changes nothing, i.e. one more to confirm.
+            for (;;) {
+                int wp = 0, carryB = -1;
+                for (int base = 0; base < m; base += 31) {
+                    const int e = base + lane;
+                    const unsigned v = (e < m) ? (buf[e] & 0x7fffffffu) : 0u;
+                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+                    const bool kp = round_step(e < m, e + 1 < m, v, x, x * x + g * g, Y, lane, n, carryB).keep;
+                    const unsigned bal = __ballot_sync(0xffffffffu, kp);
+                    __syncwarp();
+                    if (kp) buf[wp + __popc(bal & lt)] = v;
+                    wp += __popc(bal);
+                }
+                __syncwarp();
+                const bool removed = wp != m;
+                m = wp;
+                if (!removed) break;
+            }
         }
         if (lane == 0) rle_cnt[r] = m;
         if (flags & SRM_BF_RLE) {
@@ -433,7 +487,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 for (int q = 0; q < 2; ++q) {
                     const int e = base + 31 * q + lane;
                     const bool valid = e < m;
-                    const unsigned v = valid ? buf[e] : 0u;
+                    const unsigned v = valid ? (buf[e] & 0x7fffffffu) : 0u;
                     const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
                     const RoundStep st = round_step(valid, e + 1 < m, v, x, x * x + g * g, Y, lane, n, carryB);
                     if (st.owned) out[e] = make_int2((int)v, st.Bc + 1);
@@ -442,29 +496,31 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
         }
         if (accumulate) {
             // Per-site sums of the row's runs: run e = (B(e-1), B(e)] contributes the fp64 prefix differences of d and
-            // x*d (and x^2*d for the energy) to its site.  The prefix entries at the run ends and the site ids are
-            // fetched by cp.async into a ring of 32-run stages behind the runs in this warp's buffer.
+            // x*d (and x^2*d for the energy) to its site.  The prefix entries at the run ends and the home buckets of the
+            // sites in the pixel -> id hash are fetched by cp.async into a ring of 32-run stages behind the runs in this
+            // warp's buffer.
             unsigned char *ring = reinterpret_cast<unsigned char *>(buf + m4);
-            const int nst = min(BAND_NST, ((C - m4) * 4) / BAND_STAGE_BYTES);   // >= 1 (checked above)
+            const int nst = min(BAND_NST, ((C - m4) * 4) / stage_bytes);   // >= 1 (checked above)
             const int nbat = (m + 31) >> 5;
             const double2 *p2 = P2 + srm_pfx_row(r, n);   // tiled layout: element x at [x * SRM_PFX_TILE]
             const double *pxx = PXX + srm_pfx_row(r, n);
             unsigned char *touched = reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4);
             auto issue = [&](int b) {
-                unsigned char *st = ring + (b % nst) * BAND_STAGE_BYTES;
+                unsigned char *st = ring + (b % nst) * stage_bytes;
                 const int e = 32 * b + lane;
                 if (e < m) {
-                    const unsigned v = buf[e];
+                    const unsigned v = buf[e] & 0x7fffffffu;
                     const int x = (int)(v & 0xffffu), c = (int)(v >> 16), g = c - Y;
                     int B = n - 1;
                     if (e + 1 < m) {
-                        const unsigned vn = buf[e + 1];
+                        const unsigned vn = buf[e + 1] & 0x7fffffffu;
                         const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y;
                         B = breakpoint(xn * xn + gn * gn - (x * x + g * g), 2 * (xn - x), n);
                     }
+                    (void)c;
                     if (!ABL(8)) cp_async16(st + 16 * lane, p2 + (size_t)B * SRM_PFX_TILE);
-                    if (want_energy) cp_async8(st + 512 + 8 * lane, pxx + (size_t)B * SRM_PFX_TILE);
-                    if (!ABL(4)) cp_async4(st + 768 + 4 * lane, idmap + (size_t)c * n + x);
+                    if (!ABL(4)) cp_async16(st + 512 + 16 * lane, hash.b + srm_hash_bucket(hash, v));
+                    if (want_energy) cp_async8(st + 1024 + 8 * lane, pxx + (size_t)B * SRM_PFX_TILE);
                 }
                 cp_async_commit();   // one group per batch, empty ones included: uniform group accounting
             };
@@ -474,18 +530,21 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             for (int b = 0; b < nbat; ++b) {
                 cp_async_wait_pending(nst - 1);
                 __syncwarp();   // the stage holds every lane's entries
-                const unsigned char *st = ring + (b % nst) * BAND_STAGE_BYTES;
+                const unsigned char *st = ring + (b % nst) * stage_bytes;
                 const int e = 32 * b + lane;
                 const bool valid = e < m;
                 const double2 *sp = reinterpret_cast<const double2 *>(st);
-                const double *sx = reinterpret_cast<const double *>(st + 512);
+                const double *sx = reinterpret_cast<const double *>(st + 1024);
                 const double2 pb = (valid && !ABL(8)) ? sp[lane] : make_double2(1, 1);
                 const double2 pa = lane ? ((valid && !ABL(8)) ? sp[lane - 1] : make_double2(1, 1)) : carryP;
                 const double xb = (valid && want_energy) ? sx[lane] : 0, xa = lane ? ((valid && want_energy) ? sx[lane - 1] : 0) : carryXX;
-                int id = valid ? (ABL(4) ? (e + 37 * r) % Kcap : reinterpret_cast<const int *>(st + 768)[lane]) : 0;
                 carryP = sp[31]; carryXX = want_energy ? sx[31] : 0;   // broadcast reads; only full batches have a successor
                 if (valid) {
-                    const unsigned v = buf[e];
+                    const unsigned v = buf[e] & 0x7fffffffu;
+                    // every label is a live site, so the lookup succeeds; it leaves the home bucket for < 1 % of the sites
+                    const int id = ABL(4) ? (e + 37 * r) % Kcap
+                                          : max(srm_hash_find_from(hash, v, srm_hash_bucket(hash, v),
+                                                                   reinterpret_cast<const uint4 *>(st + 512)[lane]), 0);
                     const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
                     const double W = pb.x - pa.x, X = pb.y - pa.y;
                     double *a = acc + 4 * (size_t)id;
@@ -515,7 +574,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     }
 }
 
-// Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62 (and, when accumulating, one 896-byte
+// Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62 (and, when accumulating, one 1024 / 1280-byte
 // stage of the prefix ring).  Rows of an n-wide grid with the BASELINE site densities have ~n/26 runs (316 at
 // 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
 static int band_bufcap(int n) { return n <= 8192 ? BAND_C8K : n <= 16384 ? 1280 : 1792; }
@@ -574,19 +633,19 @@ static int band_rpw(int nrows) {
 template <int RPW, int C>
 static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, const short *up, const short *dn, SrmGrid g,
                             int CL, int2 *rle, int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX,
-                            const int *idmap, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
+                            SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int nbands = g.nrows() / (BAND_NW * RPW);
-    SRM_COUNT(), k_band<RPW, C><<<nbands, BAND_NT, smem, st>>>(bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2, PXX,
-                                                              idmap, acc, Kcap, ctl, flags, dbg);
+    srm_launch_pdl(st, dim3(nbands), dim3(BAND_NT), smem, k_band<RPW, C>, bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2,
+                   PXX, hash, acc, Kcap, ctl, flags, dbg);
 }
 
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
+                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
                             double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int CL = band_cap(g.n);
     const size_t smem = band_smem(g.n, CL);
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
-#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, idmap, acc, Kcap, ctl, flags, dbg
+#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, hash, acc, Kcap, ctl, flags, dbg
     if (C == BAND_C8K) { if (rpw == 1) band_launch_one<1, BAND_C8K>(BAND_ARGS); else band_launch_one<2, BAND_C8K>(BAND_ARGS); }
     else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
     else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }

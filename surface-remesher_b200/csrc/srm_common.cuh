@@ -58,6 +58,48 @@ __device__ __forceinline__ int srm_choose_col(int U, int D, int Y) {
     return ((D >> SRM_TIE_BAND_SHIFT) == (Y >> SRM_TIE_BAND_SHIFT)) ? D : U;
 }
 
+// ---- pixel -> site-id hash (replaces the two image-sized int maps of round 1: site ids and dedupe claims).
+// Buckets of two {key, id} pairs (16 bytes, one load); key = packed pixel (x | y << 16), empty = 0xffffffff with id
+// 0xffffffff (all-ones bytes: a plain memset clears a table; ids are compared as unsigned).  Open addressing over buckets, no deletions inside a step: an empty slot ends a probe sequence.  Two tables
+// alternate by iteration parity: the update of iteration t claims the new pixels in table (t+1)&1 with atomicMin(id)
+// (the smallest id keeps a contested pixel, the others become holes), which is then the id lookup of iteration t+1.
+#define SRM_HEMPTY 0xffffffffu
+struct SrmHash {
+    uint4 *b = nullptr;    // buckets
+    unsigned mask = 0;     // buckets - 1 (power of two)
+    int shift = 32;        // 32 - log2(buckets)
+};
+__device__ __forceinline__ unsigned srm_hash_bucket(const SrmHash &H, unsigned key) { return (key * 2654435761u) >> H.shift; }
+
+// id stored for `key` given its (already loaded) home bucket e; probes on only if both slots hold other keys.
+__device__ __forceinline__ int srm_hash_find_from(const SrmHash &H, unsigned key, unsigned b, uint4 e) {
+    for (unsigned probe = 0; probe <= H.mask; ++probe) {
+        if (e.x == key) return (int)e.y;
+        if (e.z == key) return (int)e.w;
+        if (e.x == SRM_HEMPTY || e.z == SRM_HEMPTY) return -1;
+        b = (b + 1) & H.mask;
+        e = H.b[b];
+    }
+    return -1;
+}
+__device__ __forceinline__ int srm_hash_find(const SrmHash &H, unsigned key) {
+    const unsigned b = srm_hash_bucket(H, key);
+    return srm_hash_find_from(H, key, b, H.b[b]);
+}
+// insert-or-min: after all claims of a step, the entry of `key` holds the smallest claiming id
+__device__ __forceinline__ void srm_hash_claim(const SrmHash &H, unsigned key, int id) {
+    unsigned b = srm_hash_bucket(H, key);
+    for (unsigned probe = 0; probe <= H.mask; ++probe) {
+        unsigned *w = reinterpret_cast<unsigned *>(H.b + b);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const unsigned old = atomicCAS(w + 2 * s, SRM_HEMPTY, key);
+            if (old == SRM_HEMPTY || old == key) { atomicMin(w + 2 * s + 1, (unsigned)id); return; }
+        }
+        b = (b + 1) & H.mask;
+    }
+}
+
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -89,16 +131,53 @@ struct SrmPeers {
 extern long long g_srm_launches;
 #define SRM_COUNT() ((void)__sync_fetch_and_add(&g_srm_launches, 1ll))
 
+// ---- Programmatic dependent launch (PDL): the kernels of the Lloyd loop are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so that a kernel's CTAs are scheduled while its predecessor
+// drains instead of after the usual kernel-boundary gap.  Contract: every such kernel executes srm_pdl_enter() as its
+// FIRST statement on every path (it must not return, nor touch global memory, before it): griddepcontrol.wait blocks
+// until the preceding grid has completed and its writes are visible, so the chain stays transitively ordered;
+// griddepcontrol.launch_dependents then lets the successor be scheduled as soon as all CTAs of this grid are resident.
+// Without the launch attribute both instructions are no-ops.  SRM_PDL=0 in the environment disables the attribute.
+__device__ __forceinline__ void srm_pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool srm_pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t srm_launch_pdl(cudaStream_t st, dim3 grid, dim3 block, size_t smem, void (*kern)(KArgs...), Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = srm_pdl_enabled() ? 1 : 0;
+    SRM_COUNT();
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- launchers (host), one per pipeline stage; all asynchronous on `st`.
 struct SrmGrid {           // geometry of one context
     int n, row0, row1;
     int nrows() const { return row1 - row0; }
 };
 
-void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
-                     int *claim, int respect_stop, int row0, int row1, int *edge);
-void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop, int row0, int row1, const int *edge);
+// Per-iteration device state that alternates by iteration parity (cur = it & 1 is read by the labelling, next is
+// cleared by the carry kernel and filled by the update): site bitmap, band edges, pixel -> id hash.
+struct SrmStep {
+    const uint32_t *bits;   // site bitmap of this iteration, indexed [(y >> 5) * n + x] (band contexts: own word rows)
+    const int *edge;        // row bands: per column nearest site row above / below the band (2n ints), else nullptr
+    SrmHash hash;           // pixel -> id of this iteration's sites
+    uint32_t *bits_next;    // next iteration's buffers
+    int *edge_next;
+    SrmHash hash_next;
+};
+
+// Build bitmap / edges / hash of buffer set `cur` from a site list (after srm_set_sites / srm_set_site_map).
+void srm_launch_init_sites(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, size_t bits_words,
+                           int *edge, SrmHash hash, int row0, int row1);
+// Carries of the current bitmap; also clears the next iteration's bitmap / edges / hash and the robust-path row list.
+void srm_launch_carry(cudaStream_t st, const SrmStep &s, int n, short *up, short *dn, SrmCtl *ctl, int respect_stop,
+                      int row0, int row1);
 // fused fast path (srm_band.cu)
 cudaError_t srm_band_setup(int n);
 // flags of the band kernel
@@ -110,23 +189,24 @@ enum {
     SRM_BF_TOUCH = 16    // mark the sites this rank contributed to (read by the peer-memory all-reduce)
 };
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, const int *idmap,
+                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
                             double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg = 0);
 // robust path, driven by a row list (rows == nullptr: every row of the band)
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                            int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
-                           const int *idmap, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
+                           SrmHash hash, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
                            int respect_stop);
 cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels);
 cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes
 
 void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX);
 void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
-                    const int *idmap, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
+                    SrmHash hash, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
                     const SrmCtl *ctl, int want_energy, int respect_stop);
+// Site update (two kernels): new positions + claims in s.hash_next, then winners -> sites_out / s.bits_next / s.edge_next.
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
-                       int stop_rule, int respect_stop, SrmPeers peers = SrmPeers());
+                       const unsigned char *mask, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
+                       int want_energy, int stop_rule, int respect_stop, SrmPeers peers = SrmPeers());
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop);
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
                                int *blockoff, int *total_out, int count_only);

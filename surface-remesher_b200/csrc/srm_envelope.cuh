@@ -94,8 +94,8 @@ __device__ __forceinline__ void env_merge(const EnvSmem &s, int g0, int gm, int 
 // prefix differences of d, x*d (and x^2*d for the energy) to its site (role of kernelTotal_X +
 // kernelScan_Y, gcvt.cu:591-732, and of kernelCalcEnergy, :788-802).  Returns the lane's energy part.
 __device__ __forceinline__ double acc_row(const int2 *rr, int cnt, const double2 *__restrict__ p2,
-                                          const double *__restrict__ pxx, const int *__restrict__ idmap, int n, int Y,
-                                          double *__restrict__ acc, int Kcap, int want_energy, int lane, int abl = 0) {
+                                          const double *__restrict__ pxx, const SrmHash &hash, int n, int Y,
+                                          double *__restrict__ acc, int Kcap, int want_energy, int lane) {
     unsigned char *touched = reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4);  // per-site "this rank contributed"
     double e_loc = 0;
     double2 carry = make_double2(0, 0);  // prefix at the end of the previous run
@@ -120,14 +120,14 @@ __device__ __forceinline__ double acc_row(const int2 *rr, int cnt, const double2
         if (act) {
             const double W = pb.x - pa.x, X = pb.y - pa.y;
             const int sx = srm_x(v.x), sy = srm_y(v.x);
-            const int id = (abl & 4) ? (e & 1023) : idmap[(size_t)sy * n + sx];
-            double *a = acc + 4 * (size_t)id;
-            if (!(abl & 2)) {
+            const int id = srm_hash_find(hash, (unsigned)v.x);   // every label is a live site: always found
+            double *a = acc + 4 * (size_t)max(id, 0);
+            if (id >= 0) {
                 atomicAdd(a, W);
                 atomicAdd(a + 1, X);
                 atomicAdd(a + 2, (double)Y * W);
                 touched[id] = 1;
-            } else if (W == -1.0) a[3] = X;  // keep the loads alive
+            }
             if (want_energy) {
                 const int dy = sy - Y;
                 e_loc += (xb - xa) - 2.0 * (double)sx * X + (double)(sx * sx + dy * dy) * W;

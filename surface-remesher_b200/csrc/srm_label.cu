@@ -22,36 +22,41 @@
 // Row-band contexts fill only their own word rows of the bitmap; what lies outside the band enters through two
 // per-column edge values (the nearest site row above / below the band), which seed the band's carry scan.  This is
 // what kernelPropagateInterband (gcvt.cu:121-170) hands from band to band, here straight from the replicated site list.
-#define EDGE_NONE_TOP ((int)0x80808080)   // byte pattern of the per-iteration memset: "no site above" (< 0)
+#define EDGE_NONE_TOP ((int)0x80808080)   // "no site above" (< 0)
 #define EDGE_NONE_BOT ((int)0x7f7f7f7f)   // "no site below" (> 32767)
 
-__global__ void k_bits(const int *__restrict__ sites, SrmCtl *ctl, int n, uint32_t *bits, int *idmap, int *claim,
-                       int respect_stop, int row0, int row1, int *edge) {
-    if (respect_stop && ctl->stop) return;
-    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->ovf = 0; ctl->band_ticket = 0; }  // robust-path row list, band ticket
-    int id = blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= ctl->K) return;
-    int p = sites[id];
-    if (p == SRM_SENT) return;  // merged away
-    int x = srm_x(p), y = srm_y(p);
+// One site into the per-iteration structures: bitmap bit (own rows) or band edge.
+__device__ __forceinline__ void srm_place_site(int p, int n, uint32_t *bits, int *edge, int row0, int row1) {
+    const int x = srm_x(p), y = srm_y(p);
     if (y >= row0 && y < row1) atomicOr(&bits[(size_t)(y >> 5) * n + x], 1u << (y & 31));
     else if (y < row0) atomicMax(&edge[x], y);
     else atomicMin(&edge[n + x], y);
-    size_t i = (size_t)y * n + x;
-    idmap[i] = id;      // site pixel -> accumulator slot
-    claim[i] = INT_MAX; // reset the dedupe claim left by the previous update
 }
 
-void srm_launch_bits(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, int *idmap,
-                     int *claim, int respect_stop, int row0, int row1, int *edge) {
-    // the memsets are skipped after a stop only in effect (bits are then unused until the final labelling
-    // rebuilds them), so they can stay unconditional
-    cudaMemsetAsync(bits + (size_t)(row0 >> 5) * n, 0, (size_t)((row1 - row0) >> 5) * n * sizeof(uint32_t), st);
-    if (row0 > 0 || row1 < n) {
-        cudaMemsetAsync(edge, 0x80, (size_t)n * sizeof(int), st);
-        cudaMemsetAsync(edge + n, 0x7f, (size_t)n * sizeof(int), st);
-    }
-    SRM_COUNT(), k_bits<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, idmap, claim, respect_stop, row0, row1, edge);
+// Initial build from a site list (srm_set_sites / srm_set_site_map); inside the loop the update kernel places the
+// surviving sites of the next iteration itself (srm_lloyd.cu).  The buffers were cleared by the launcher.
+__global__ void k_init_sites(const int *__restrict__ sites, const SrmCtl *__restrict__ ctl, int n, uint32_t *bits, int *edge,
+                             SrmHash hash, int row0, int row1) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= ctl->K) return;
+    const int p = sites[id];
+    if (p == SRM_SENT) return;
+    srm_place_site(p, n, bits, edge, row0, row1);
+    srm_hash_claim(hash, (unsigned)p, id);
+}
+
+__global__ void k_fill_edge(int *edge, int n) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x < n) { edge[x] = EDGE_NONE_TOP; edge[n + x] = EDGE_NONE_BOT; }
+}
+
+void srm_launch_init_sites(cudaStream_t st, const int *sites, SrmCtl *ctl, int Kcap, int n, uint32_t *bits, size_t bits_words,
+                           int *edge, SrmHash hash, int row0, int row1) {
+    // bits: base pointer for absolute word-row indexing; the context's own words start at (row0 >> 5) * n
+    cudaMemsetAsync(bits + (size_t)(row0 >> 5) * n, 0, bits_words * sizeof(uint32_t), st);
+    cudaMemsetAsync(hash.b, 0xff, ((size_t)hash.mask + 1) * sizeof(uint4), st);
+    if (edge) SRM_COUNT(), k_fill_edge<<<(n + 255) / 256, 256, 0, st>>>(edge, n);
+    SRM_COUNT(), k_init_sites<<<(max(Kcap, 1) + 255) / 256, 256, 0, st>>>(sites, ctl, n, bits, edge, hash, row0, row1);
 }
 
 __device__ __forceinline__ int edge_top(const int *edge, int x) {
@@ -65,23 +70,39 @@ __device__ __forceinline__ int edge_bot(const int *edge, int n, int x) {
     return v > 32767 ? SRM_MARK : v;
 }
 
+// Every carry kernel also prepares the NEXT iteration's buffers (they are filled by the update kernels later in this
+// iteration): it zeroes the bitmap words at the indices it scans, and clears the hash table, the band edges and the
+// robust-path row counter grid-wide.  This replaces the per-iteration memsets and the k_bits kernel of round 1.
+__device__ __forceinline__ void carry_clear_next(const SrmStep &s, int n, SrmCtl *ctl, size_t tid, size_t nthreads) {
+    if (tid == 0) ctl->ovf = 0;
+    const uint4 e = make_uint4(SRM_HEMPTY, 0xffffffffu, SRM_HEMPTY, 0xffffffffu);
+    for (size_t i = tid; i <= (size_t)s.hash_next.mask; i += nthreads) s.hash_next.b[i] = e;
+    if (s.edge_next)
+        for (size_t x = tid; x < (size_t)n; x += nthreads) { s.edge_next[x] = EDGE_NONE_TOP; s.edge_next[n + x] = EDGE_NONE_BOT; }
+}
+
 // Generic form (any n): one thread per column, one sweep per direction.
-__global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__restrict__ up, short *__restrict__ dn,
-                        const SrmCtl *__restrict__ ctl, int respect_stop, int jbeg, int jend, const int *edge) {
+__global__ void k_carry_any(SrmStep s, int n, short *__restrict__ up, short *__restrict__ dn, SrmCtl *ctl, int respect_stop,
+                            int jbeg, int jend) {
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
+    const uint32_t *__restrict__ bits = s.bits;
+    const size_t tid = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    carry_clear_next(s, n, ctl, tid, (size_t)gridDim.x * gridDim.y * blockDim.x);
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= n) return;
     if (blockIdx.y == 0) {
-        int last = edge_top(edge, x);
+        int last = edge_top(s.edge, x);
 #pragma unroll 8
         for (int j = jbeg; j < jend; ++j) {
             size_t o = (size_t)j * n + x;
             uint32_t w = bits[o];
             up[o] = (short)last;
+            s.bits_next[o] = 0u;
             if (w) last = 32 * j + 31 - __clz(w);
         }
     } else {
-        int next = edge_bot(edge, n, x);
+        int next = edge_bot(s.edge, n, x);
 #pragma unroll 8
         for (int j = jend - 1; j >= jbeg; --j) {
             size_t o = (size_t)j * n + x;
@@ -100,11 +121,14 @@ __global__ void k_carry_any(const uint32_t *__restrict__ bits, int n, short *__r
 // writes both carries of its words.
 // WPS words per segment are held in registers (<= 32: more spills), CARRY_SEG = 8, 16 or 32 segments per column.
 template <int WPS, int CARRY_SEG>
-__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__restrict__ bits, int n, short *__restrict__ up,
-                                                          short *__restrict__ dn, const SrmCtl *__restrict__ ctl,
-                                                          int respect_stop, int jbeg, const int *edge) {
+__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(SrmStep s, int n, short *__restrict__ up, short *__restrict__ dn,
+                                                          SrmCtl *ctl, int respect_stop, int jbeg) {
     __shared__ short s_last[CARRY_SEG][32], s_first[CARRY_SEG][32];
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
+    const uint32_t *__restrict__ bits = s.bits;
+    carry_clear_next(s, n, ctl, (size_t)blockIdx.x * (32 * CARRY_SEG) + threadIdx.y * 32 + threadIdx.x,
+                     (size_t)gridDim.x * (32 * CARRY_SEG));
     const int x = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
     const int j0 = jbeg + seg * WPS;
     uint32_t w[WPS];
@@ -112,6 +136,7 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
 #pragma unroll
     for (int k = 0; k < WPS; ++k) {
         w[k] = bits[(size_t)(j0 + k) * n + x];
+        s.bits_next[(size_t)(j0 + k) * n + x] = 0u;
         if (w[k]) {
             last = 32 * (j0 + k) + 31 - __clz(w[k]);
             if (first == SRM_MARK) first = 32 * (j0 + k) + __ffs(w[k]) - 1;
@@ -120,7 +145,7 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
     s_last[seg][threadIdx.x] = (short)last;
     s_first[seg][threadIdx.x] = (short)first;
     __syncthreads();
-    int cu = edge_top(edge, x), cd = edge_bot(edge, n, x);  // nearest site row above / below this segment
+    int cu = edge_top(s.edge, x), cd = edge_bot(s.edge, n, x);  // nearest site row above / below this segment
     for (int q = 0; q < seg; ++q) { const int v = s_last[q][threadIdx.x]; if (v != SRM_MARK) cu = v; }
     for (int q = CARRY_SEG - 1; q > seg; --q) { const int v = s_first[q][threadIdx.x]; if (v != SRM_MARK) cd = v; }
 #pragma unroll
@@ -139,18 +164,21 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry(const uint32_t *__rest
 // carries, down carries; the re-reads hit L2).  For long columns (n > 8192 on one GPU), where 32+ words per thread
 // would spill: 32 segments of nw/32 words.
 template <int CARRY_SEG>
-__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry_loop(const uint32_t *__restrict__ bits, int n,
-                                                               short *__restrict__ up, short *__restrict__ dn,
-                                                               const SrmCtl *__restrict__ ctl, int respect_stop,
-                                                               int jbeg, int wps, const int *edge) {
+__global__ void __launch_bounds__(32 * CARRY_SEG) k_carry_loop(SrmStep s, int n, short *__restrict__ up, short *__restrict__ dn,
+                                                               SrmCtl *ctl, int respect_stop, int jbeg, int wps) {
     __shared__ short s_last[CARRY_SEG][32], s_first[CARRY_SEG][32];
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
+    const uint32_t *__restrict__ bits = s.bits;
+    carry_clear_next(s, n, ctl, (size_t)blockIdx.x * (32 * CARRY_SEG) + threadIdx.y * 32 + threadIdx.x,
+                     (size_t)gridDim.x * (32 * CARRY_SEG));
     const int x = blockIdx.x * 32 + threadIdx.x, seg = threadIdx.y;
     const int j0 = jbeg + seg * wps;
     int last = SRM_MARK, first = SRM_MARK;
 #pragma unroll 4
     for (int k = 0; k < wps; ++k) {
         const uint32_t w = bits[(size_t)(j0 + k) * n + x];
+        s.bits_next[(size_t)(j0 + k) * n + x] = 0u;
         if (w) {
             last = 32 * (j0 + k) + 31 - __clz(w);
             if (first == SRM_MARK) first = 32 * (j0 + k) + __ffs(w) - 1;
@@ -159,7 +187,7 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry_loop(const uint32_t *_
     s_last[seg][threadIdx.x] = (short)last;
     s_first[seg][threadIdx.x] = (short)first;
     __syncthreads();
-    int cu = edge_top(edge, x), cd = edge_bot(edge, n, x);
+    int cu = edge_top(s.edge, x), cd = edge_bot(s.edge, n, x);
     for (int q = 0; q < seg; ++q) { const int v = s_last[q][threadIdx.x]; if (v != SRM_MARK) cu = v; }
     for (int q = CARRY_SEG - 1; q > seg; --q) { const int v = s_first[q][threadIdx.x]; if (v != SRM_MARK) cd = v; }
 #pragma unroll 4
@@ -178,25 +206,30 @@ __global__ void __launch_bounds__(32 * CARRY_SEG) k_carry_loop(const uint32_t *_
     }
 }
 
-void srm_launch_carry(cudaStream_t st, const uint32_t *bits, int n, short *up, short *dn, const SrmCtl *ctl,
-                      int respect_stop, int row0, int row1, const int *edge) {
-    // Carries of the band's own word rows only; the rest of the column is summarised by the edge values that k_bits
+void srm_launch_carry(cudaStream_t st, const SrmStep &s, int n, short *up, short *dn, SrmCtl *ctl, int respect_stop,
+                      int row0, int row1) {
+    // Carries of the band's own word rows only; the rest of the column is summarised by the edge values that the update
     // collected (whole-grid contexts: no edges).  8 segments per column, words in registers.
     const int jbeg = row0 >> 5, jend = row1 >> 5, nw = jend - jbeg;
-    const int *e = (row0 > 0 || row1 < n) ? edge : nullptr;
     const int wps = (nw % 8) ? 0 : nw / 8;
     dim3 grid(n / 32), block(32, 8);
-    if (wps > 32 && nw % 32 == 0) {   // long columns: 32 segments, looped
-        SRM_COUNT(), k_carry_loop<32><<<grid, dim3(32, 32), 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, nw / 32, e);
+    if (nw % 32 == 0 && nw / 32 >= 4) {
+        // long columns: 32 segments per column (1024 threads per CTA), words in registers up to 16 per thread (a
+        // 32-word segment needs 206 registers: one CTA per SM and 12 % of the warps, round-2 ncu capture), looped beyond
+        const int w32 = nw / 32;
+#define CARRY32(W) if (w32 == W) { srm_launch_pdl(st, grid, dim3(32, 32), 0, k_carry<W, 32>, s, n, up, dn, ctl, respect_stop, jbeg); return; }
+        CARRY32(4) CARRY32(8) CARRY32(16)
+#undef CARRY32
+        srm_launch_pdl(st, grid, dim3(32, 32), 0, k_carry_loop<32>, s, n, up, dn, ctl, respect_stop, jbeg, w32);
         return;
     }
-#define CARRY_CASE(W) if (wps == W) { SRM_COUNT(), k_carry<W, 8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, e); return; }
-    CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8) CARRY_CASE(16) CARRY_CASE(32)
+#define CARRY_CASE(W) if (wps == W) { srm_launch_pdl(st, grid, block, 0, k_carry<W, 8>, s, n, up, dn, ctl, respect_stop, jbeg); return; }
+    CARRY_CASE(1) CARRY_CASE(2) CARRY_CASE(3) CARRY_CASE(4) CARRY_CASE(8)
     if (wps > 0) {   // other band heights (work-balanced row bands): 8 segments, looped
-        SRM_COUNT(), k_carry_loop<8><<<grid, block, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, wps, e);
+        srm_launch_pdl(st, grid, block, 0, k_carry_loop<8>, s, n, up, dn, ctl, respect_stop, jbeg, wps);
         return;
     }
-    SRM_COUNT(), k_carry_any<<<dim3((n + 63) / 64, 2), 64, 0, st>>>(bits, n, up, dn, ctl, respect_stop, jbeg, jend, e);
+    srm_launch_pdl(st, dim3((n + 63) / 64, 2), dim3(64), 0, k_carry_any, s, n, up, dn, ctl, respect_stop, jbeg, jend);
 #undef CARRY_CASE
 }
 
@@ -241,13 +274,14 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
                                                 const short *__restrict__ dn, int n, int row0, int nrows, int2 *rle,
                                                 int *__restrict__ rle_cnt, const int *__restrict__ rows,
                                                 const int *__restrict__ count, const double2 *__restrict__ P2,
-                                                const double *__restrict__ PXX, const int *__restrict__ idmap,
+                                                const double *__restrict__ PXX, SrmHash hash,
                                                 double *__restrict__ acc, int Kcap, const SrmCtl *__restrict__ ctl,
                                                 int accumulate, int want_energy, int respect_stop) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
     __shared__ int row_total;   // runs of the row (its own word: wtot[] is still being read by slower warps)
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
     EnvSmem s;
     s.x = (unsigned short *)smem_raw;
@@ -330,7 +364,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
         }
         __syncthreads();
         if (accumulate && w == 0) {
-            double e_loc = acc_row(rle + (size_t)r * n, row_total, P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, Y, acc,
+            double e_loc = acc_row(rle + (size_t)r * n, row_total, P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, Y, acc,
                                    Kcap, want_energy, lane);
             if (want_energy) {
                 e_loc = warp_sum(e_loc);
@@ -356,11 +390,11 @@ cudaError_t srm_label_setup(int n) {
 
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
                            int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
-                           const int *idmap, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
+                           SrmHash hash, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
                            int respect_stop) {
     const int grid = rows ? 148 : g.nrows();
-    SRM_COUNT(), k_row<<<grid, ROW_NT, row_smem_bytes(g.n), st>>>(bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows, count, P2,
-                                                     PXX, idmap, acc, Kcap, ctl, accumulate, want_energy, respect_stop);
+    srm_launch_pdl(st, dim3(grid), dim3(ROW_NT), row_smem_bytes(g.n), k_row, bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows,
+                   count, P2, PXX, hash, acc, Kcap, ctl, accumulate, want_energy, respect_stop);
     return cudaGetLastError();
 }
 

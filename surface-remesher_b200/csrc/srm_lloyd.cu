@@ -73,7 +73,7 @@ void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, do
 // Robust-path accumulation: one warp per listed row (rows == nullptr: all rows of the band).
 __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt,
                                                 const double2 *__restrict__ P2, const double *__restrict__ PXX,
-                                                const int *__restrict__ idmap, int n, int row0, int nrows,
+                                                SrmHash hash, int n, int row0, int nrows,
                                                 double *__restrict__ acc, int Kcap, const int *__restrict__ rows,
                                                 const int *__restrict__ count, const SrmCtl *__restrict__ ctl,
                                                 int want_energy, int respect_stop) {
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
     double e_loc = 0;
     for (int q = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5); q < total; q += nwarps) {
         const int r = rows ? rows[q] : q;
-        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), idmap, n, row0 + r, acc,
+        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, row0 + r, acc,
                          Kcap, want_energy, lane);
     }
     if (want_energy) {
@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
 }
 
 void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
-                    const int *idmap, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
+                    SrmHash hash, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
                     const SrmCtl *ctl, int want_energy, int respect_stop) {
     const int rows_per_block = ACC_NT / 32;
     const int grid = rows ? 148 : (g.nrows() + rows_per_block - 1) / rows_per_block;
-    SRM_COUNT(), k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, idmap, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
+    SRM_COUNT(), k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, hash, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
                                    want_energy, respect_stop);
 }
 
@@ -137,10 +137,12 @@ void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, i
 
 // kernelUpdateSites (gcvt.cu:753-781): centroid, over-relaxation, round, clamp, reject.  The float
 // expression is written with the roundings nvcc produced for the reference (FADD, FFMA, FADD,
-// F2I.TRUNC; checked in the SASS of oracle/_ref).  Collisions: every site claims its target pixel
-// with atomicMin(id); the smallest id survives and the others become holes (SRM_SENT) in the list —
-// the reference merges sites the same way, by overwriting one pixel (gcvt.cu:779-780).  The list is
-// never compacted, so ids (accumulator slots) are stable and identical on every rank.
+// F2I.TRUNC; checked in the SASS of oracle/_ref).  Collisions: every site claims its target pixel in
+// the NEXT iteration's pixel -> id hash with atomicMin(id); the smallest id survives and the others
+// become holes (SRM_SENT) in the list — the reference merges sites the same way, by overwriting one
+// pixel (gcvt.cu:779-780).  The list is never compacted, so ids (accumulator slots) are stable and
+// identical on every rank.  The survivors are then placed into the next iteration's site bitmap / band
+// edges, so no separate "sites -> bitmap" kernel runs inside the loop.
 __device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const volatile int *)p; }
 
 // Fused all-reduce (row bands on several GPUs): every rank signals "my accumulators of iteration it are complete"
@@ -150,6 +152,7 @@ __device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const vo
 // double-buffered by iteration parity; a buffer is cleared one iteration after its use, when every peer has
 // provably finished reading it (they have signalled the next iteration).
 __global__ void k_signal(SrmCtl *ctl, SrmPeers p, int respect_stop) {
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
     const int target = (ctl->epoch << 20) | (ctl->it + 1);
     __threadfence_system();
@@ -157,12 +160,13 @@ __global__ void k_signal(SrmCtl *ctl, SrmPeers p, int respect_stop) {
 }
 
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop) {
-    if (peers.world > 1) SRM_COUNT(), k_signal<<<1, 32, 0, st>>>(ctl, peers, respect_stop);
+    if (peers.world > 1) srm_launch_pdl(st, dim3(1), dim3(32), 0, k_signal, ctl, peers, respect_stop);
 }
 
 __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const float *__restrict__ density,
                              const unsigned char *__restrict__ mask, int n, SrmCtl *ctl, int *__restrict__ newpos,
-                             int *claim, int respect_stop, SrmPeers peers) {
+                             SrmHash claim, int respect_stop, SrmPeers peers) {
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
     if (peers.world > 1) {  // wait for every rank's accumulators of this iteration
         if (threadIdx.x == 0) {
@@ -233,27 +237,36 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
         cy = max(min(cy, n - 1), 0);
         if (density[(size_t)cy * n + cx] != 0.0f) { rx = cx; ry = cy; }
     }
-    newpos[id] = srm_pack(rx, ry);
-    atomicMin(&claim[(size_t)ry * n + rx], id);
+    const int np = srm_pack(rx, ry);
+    newpos[id] = np;
+    srm_hash_claim(claim, (unsigned)np, id);
 }
 
 #define UPD_NT 256
 // Resolve the claims, clear the accumulators, and — in the last block to finish — run the loop control of
 // gCVT (gcvt.cu:1116-1140) on device: latch the energy, count the iteration, every 10th iteration update omega
 // and apply the stopping rule.
-__global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict__ newpos, const int *__restrict__ claim,
-                                                           int n, SrmCtl *ctl, int *__restrict__ sites_out,
-                                                           double *acc, int Kcap, int want_energy, int stop_rule,
-                                                           int respect_stop, SrmPeers peers) {
+__global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict__ newpos, SrmHash claim, int n, int row0,
+                                                           int row1, uint32_t *bits_next, int *edge_next, SrmCtl *ctl,
+                                                           int *__restrict__ sites_out, double *acc, int Kcap,
+                                                           int want_energy, int stop_rule, int respect_stop,
+                                                           SrmPeers peers) {
     __shared__ int is_last;
+    srm_pdl_enter();
     if (respect_stop && ctl->stop) return;  // set only by a previous launch's last block
     if (ctl->p2p_timeout) return;           // k_update_pos gave up waiting for a peer: leave the sites as they are
     const int id = blockIdx.x * UPD_NT + threadIdx.x;
     int alive = 0;
     if (id < ctl->K) {
         const int p = newpos[id];
-        if (p != SRM_SENT) alive = claim[(size_t)srm_y(p) * n + srm_x(p)] == id;
+        if (p != SRM_SENT) alive = srm_hash_find(claim, (unsigned)p) == id;
         sites_out[id] = alive ? p : SRM_SENT;
+        if (alive) {   // into the next iteration's bitmap (own rows) or band edges
+            const int x = srm_x(p), y = srm_y(p);
+            if (y >= row0 && y < row1) atomicOr(&bits_next[(size_t)(y >> 5) * n + x], 1u << (y & 31));
+            else if (y < row0) atomicMax(&edge_next[x], y);
+            else atomicMin(&edge_next[n + x], y);
+        }
         // clear for a later iteration: the buffer just used (single GPU), or the other one of the pair (peers may
         // still be reading the current one; the other one was last read an iteration ago)
         double *abase = acc + (peers.world > 1 ? (size_t)(peers.parity ^ 1) * peers.stride : 0);
@@ -307,13 +320,14 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
 }
 
 void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, int n, SrmCtl *ctl, int Kcap, int *newpos, int *claim, int want_energy,
-                       int stop_rule, int respect_stop, SrmPeers peers) {
+                       const unsigned char *mask, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
+                       int want_energy, int stop_rule, int respect_stop, SrmPeers peers) {
     // acc: single GPU: the accumulator buffer; peers: the BASE of this rank's buffer pair
     const int k1 = Kcap > 0 ? Kcap : 1;
-    SRM_COUNT(), k_update_pos<<<(k1 + 255) / 256, 256, 0, st>>>(sites_in, acc, density, mask, n, ctl, newpos, claim, respect_stop, peers);
-    SRM_COUNT(), k_update_resolve<<<(k1 + UPD_NT - 1) / UPD_NT, UPD_NT, 0, st>>>(newpos, claim, n, ctl, sites_out, acc, Kcap, want_energy,
-                                                                     stop_rule, respect_stop, peers);
+    srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, density, mask, g.n, ctl, newpos,
+                   s.hash_next, respect_stop, peers);
+    srm_launch_pdl(st, dim3((k1 + UPD_NT - 1) / UPD_NT), dim3(UPD_NT), 0, k_update_resolve, (const int *)newpos, s.hash_next, g.n, g.row0,
+                   g.row1, s.bits_next, s.edge_next, ctl, sites_out, acc, Kcap, want_energy, stop_rule, respect_stop, peers);
 }
 
 // ------------------------------------------------------------------ multires (coarse-to-fine, gcvt.cu:485-511)
