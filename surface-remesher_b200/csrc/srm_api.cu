@@ -18,6 +18,7 @@
 #include <algorithm>
 #include <dlfcn.h>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -426,23 +427,62 @@ static int density_ready(srm_ctx *c) {
     return SRM_OK;
 }
 
+// Pinned (cudaHostAlloc / cudaHostRegister) memory is DMA-able as it is; pageable memory goes through the staging
+// pipeline of srm_host.cu.
+static bool host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int upload(srm_ctx *c, void *dst, const void *src, size_t bytes, int on_device) {
+    if (on_device) { CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream)); return SRM_OK; }
+    if (host_ptr_is_pinned(src) || bytes < (1u << 20)) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));   // the caller may reuse its buffer when we return
+        return SRM_OK;
+    }
+    CK(srm_h2d_pageable(dst, src, bytes, c->stream));
+    return SRM_OK;
+}
+
 extern "C" int srm_set_density(srm_ctx *c, const float *density, int on_device) {
     if (!c || !density) return fail(SRM_ERR_ARG, "srm_set_density: null argument");
     CK(cudaSetDevice(c->device));
-    CK(cudaMemcpyAsync(c->density, density, c->N * sizeof(float),
-                       on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    if (!on_device) CK(cudaStreamSynchronize(c->stream));  // pageable source must stay valid
+    int rc = upload(c, c->density, density, c->N * sizeof(float), on_device);
+    if (rc) return rc;
     return density_ready(c);
+}
+
+// dense device mask from the list of constraint pixels (packed x | y << 16)
+static int set_mask_pixels(srm_ctx *c, const std::vector<int> &px) {
+    CK(cudaMemsetAsync(c->mask, 0, c->N, c->stream));
+    if (!px.empty()) {
+        int *d = nullptr;
+        CK(cudaMalloc(&d, px.size() * sizeof(int)));
+        cudaError_t e = cudaMemcpyAsync(d, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) { srm_launch_scatter_mask(c->stream, d, (int)px.size(), c->g.n, c->mask); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // px may be a local of the caller
+        cudaFree(d);
+        if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_set_mask: %s", cudaGetErrorString(e));
+    }
+    c->has_mask = true;
+    return SRM_OK;
 }
 
 extern "C" int srm_set_mask(srm_ctx *c, const unsigned char *mask, int on_device) {
     if (!c) return fail(SRM_ERR_ARG, "null ctx");
     CK(cudaSetDevice(c->device));
     if (!mask) { c->has_mask = false; return SRM_OK; }
-    CK(cudaMemcpyAsync(c->mask, mask, c->N, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
-    if (!on_device) CK(cudaStreamSynchronize(c->stream));
-    c->has_mask = true;
-    return SRM_OK;
+    if (on_device) {
+        CK(cudaMemcpyAsync(c->mask, mask, c->N, cudaMemcpyDeviceToDevice, c->stream));
+        c->has_mask = true;
+        return SRM_OK;
+    }
+    // the mask marks a few constraint pixels (generateMask, gcvt.h:143-159): scan it on the host, upload the list
+    std::vector<int> px;
+    srm_scan_mask(mask, c->g.n, px);
+    return set_mask_pixels(c, px);
 }
 
 extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device) {
@@ -450,9 +490,11 @@ extern "C" int srm_set_site_map(srm_ctx *c, const short *site_map, int on_device
     CK(cudaSetDevice(c->device));
     const int *dmap = (const int *)site_map;
     if (!on_device) {
-        if (!c->scratch_map) CK(cudaMalloc(&c->scratch_map, c->N * sizeof(int)));
-        CK(cudaMemcpyAsync(c->scratch_map, site_map, c->N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        dmap = c->scratch_map;
+        // a seed map holds a handful of sites in 4 B/px: scan it on the host (row-major order = the order of the device
+        // compaction below, so the site ids are the same on both paths) and upload the list
+        std::vector<int> sites;
+        srm_scan_site_map((const int *)site_map, c->N, sites);
+        return srm_set_sites(c, sites.data(), (int)sites.size(), 0);
     }
     int rc;
     srm_launch_sites_from_map(c->stream, dmap, c->N, nullptr, c->blockcnt, c->blockoff, &c->ctl->nlive, 1);
@@ -860,7 +902,10 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
         dst = c->labels;
     }
     CK(srm_launch_expand(c->stream, c->rle, c->rle_cnt, c->g, dst));
-    if (!on_device) CK(cudaMemcpyAsync(out, dst, NB * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (!on_device) {
+        if (host_ptr_is_pinned(out)) CK(cudaMemcpyAsync(out, dst, NB * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        else CK(srm_d2h_pageable(out, dst, NB * sizeof(int), c->stream));
+    }
     CK(cudaStreamSynchronize(c->stream));
     return SRM_OK;
 }
@@ -897,6 +942,7 @@ static int g_cache_n = 0, g_cache_dev = -1;
 extern "C" int srm_release_cache(void) {
     std::lock_guard<std::mutex> lock(g_cache_mu);
     if (g_cache) { srm_destroy(g_cache); g_cache = nullptr; }
+    srm_host_pool_release();
     return SRM_OK;
 }
 
@@ -1009,12 +1055,20 @@ extern "C" int srm_gcvt(short *voronoi, const float *density, const unsigned cha
         if (rc) { srm_destroy(g_cache); g_cache = nullptr; }
         return rc;
     }
-    rc = srm_set_density(c, density, 0);
-    TR("density");
-    if (!rc) rc = srm_set_mask(c, mask, 0);
-    TR("mask");
-    if (!rc) rc = srm_set_site_map(c, voronoi, 0);
-    TR("site_map");
+    {   // the two sparse inputs are scanned on host threads while the density goes up through the staging pipeline
+        std::vector<int> mask_px, sites;
+        std::thread scan([&]() {
+            if (mask) srm_scan_mask(mask, n, mask_px);
+            srm_scan_site_map((const int *)voronoi, (size_t)n * n, sites);
+        });
+        rc = srm_set_density(c, density, 0);
+        scan.join();
+        TR("density+scans");
+        if (!rc) { if (mask) rc = set_mask_pixels(c, mask_px); else c->has_mask = false; }
+        TR("mask");
+        if (!rc) rc = srm_set_sites(c, sites.data(), (int)sites.size(), 0);
+        TR("sites");
+    }
     if (!rc) rc = srm_run(c, max_iter, 1, stats);
     TR("run");
     if (!rc) rc = srm_get_labels(c, voronoi, 0);

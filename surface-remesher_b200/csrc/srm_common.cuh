@@ -230,3 +230,14 @@ cudaError_t srm_launch_lift(cudaStream_t st, const int *tri_dev, const double *p
 
 cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int num_point, const int *tri, int num_tri,
                        float *density, double scale, int n);
+
+// host side of the boundary (srm_host.cu): pageable <-> device copies at PCIe speed, host scans of the sparse inputs
+#ifdef __cplusplus
+#include <vector>
+cudaError_t srm_h2d_pageable(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t after);
+cudaError_t srm_d2h_pageable(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t after);
+void srm_scan_site_map(const int *site_map, size_t N, std::vector<int> &sites);
+void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels);
+void srm_host_pool_release();
+void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, unsigned char *mask);
+#endif

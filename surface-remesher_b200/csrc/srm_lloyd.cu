@@ -362,6 +362,18 @@ void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K) {
     if (K > 0) SRM_COUNT(), k_zoom_sites<<<(K + 255) / 256, 256, 0, st>>>(in, out, K);
 }
 
+// constraint pixels found by the host scan (srm_host.cu) -> dense 1 B/px mask (cleared by the caller)
+__global__ void k_scatter_mask(const int *__restrict__ pixels, int count, int n, unsigned char *__restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int p = pixels[i];
+    mask[(size_t)srm_y(p) * n + srm_x(p)] = 1;
+}
+
+void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, unsigned char *mask) {
+    if (count > 0) SRM_COUNT(), k_scatter_mask<<<(count + 255) / 256, 256, 0, st>>>(pixels, count, n, mask);
+}
+
 // ------------------------------------------------------------------ dense seed map -> site list
 
 #define SFM_NT 256
