@@ -109,6 +109,12 @@ int srm_synchronize(srm_ctx *ctx);
 /* Inputs: full-grid arrays (n*n).  on_device != 0 means the pointer is device memory on ctx's device. */
 int srm_set_density(srm_ctx *ctx, const float *density, int on_device);
 int srm_set_mask(srm_ctx *ctx, const unsigned char *mask, int on_device); /* NULL = no constraints */
+/* Row bands without replicating the inputs: only the band's own rows of the density ((row1-row0)*n floats) ... */
+int srm_set_density_band(srm_ctx *ctx, const float *band_rows, int on_device);
+/* ... and the two full-grid bitmaps the replicated site update reads (which = 0: density != 0, 1: constraint pixels;
+ * n*n/32 words each, row y starts at word y*n/32).  After srm_set_density_band every rank holds the density bits of its
+ * own rows only: the caller exchanges the slices between the ranks (an all-gather; plumbing) before iterating. */
+int srm_shared_bits(srm_ctx *ctx, int which, void **device_ptr, size_t *num_words);
 /* Sites from a dense seed map (short2 per pixel) or from a packed list. */
 int srm_set_site_map(srm_ctx *ctx, const short *site_map, int on_device);
 int srm_set_sites(srm_ctx *ctx, const int *packed_xy, int num, int on_device);

@@ -63,6 +63,8 @@ def lib():
     L.srm_synchronize.argtypes = [p]
     L.srm_set_density.argtypes = [p, p, i]
     L.srm_set_mask.argtypes = [p, p, i]
+    L.srm_set_density_band.argtypes = [p, p, i]
+    L.srm_shared_bits.argtypes = [p, i, C.POINTER(p), C.POINTER(C.c_size_t)]
     L.srm_set_site_map.argtypes = [p, p, i]
     L.srm_set_sites.argtypes = [p, p, i, i]
     L.srm_get_sites.argtypes = [p, p, i, C.POINTER(i)]
@@ -83,7 +85,7 @@ def lib():
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
-                 "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
+                 "srm_set_density_band", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
@@ -301,6 +303,18 @@ class Context:
     def set_density(self, density):
         p, dev = _ptr(density)
         _ck(lib().srm_set_density(self._h, p, dev))
+
+    def set_density_band(self, band_rows):
+        """Row bands: only the context's own rows, (row1-row0, n) float32.  The caller then exchanges the slices of
+        shared_bits(0) between the ranks."""
+        p, dev = _ptr(band_rows)
+        _ck(lib().srm_set_density_band(self._h, p, dev))
+
+    def shared_bits(self, which):
+        """(device pointer, number of 32-bit words) of a full-grid bitmap: 0 = density != 0, 1 = constraint pixels."""
+        p, cnt = C.c_void_p(), C.c_size_t()
+        _ck(lib().srm_shared_bits(self._h, int(which), C.byref(p), C.byref(cnt)))
+        return p.value, cnt.value
 
     def set_mask(self, mask):
         if mask is None:

@@ -90,9 +90,10 @@ struct srm_ctx {
     size_t N = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    // inputs (full grid) and per-band derived data
+    // inputs: the density of the context's own rows (the prefix sums are built from it), and two full-grid bitmaps of
+    // N/8 bytes each that the replicated site update reads at arbitrary pixels: "density != 0" and "constraint pixel"
     float *density = nullptr;
-    unsigned char *mask = nullptr;
+    uint32_t *nzbits = nullptr, *maskbits = nullptr;
     bool has_mask = false, has_density = false, has_sites = false, labelled = false;
     double2 *P2 = nullptr;
     double *PXX = nullptr;
@@ -107,8 +108,9 @@ struct srm_ctx {
     uint32_t *bits_alloc[2] = {nullptr, nullptr}, *bits[2] = {nullptr, nullptr};
     short *up_alloc = nullptr, *dn_alloc = nullptr, *up = nullptr, *dn = nullptr;
     size_t band_words = 0;
-    int2 *rle = nullptr;
-    int *rle_cnt = nullptr, *labels = nullptr, *scratch_map = nullptr;
+    int2 *rle = nullptr, *row_scratch = nullptr;   // run-length pool (SrmRle), scratch rows of the robust row kernel
+    int rle_cap = 0;
+    int *rle_cnt = nullptr, *rle_off = nullptr, *labels = nullptr, *scratch_map = nullptr;
     int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
     int *edge[2] = {nullptr, nullptr};   // row bands: per column, nearest site row above / below the band (2n ints)
     SrmHash hash[2];           // pixel -> site id (and the dedupe claims of the update)
@@ -234,8 +236,9 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     c->own_stream = true;
     CKD(cudaEventCreate(&c->ev0));
     CKD(cudaEventCreate(&c->ev1));
-    CKD(cudaMalloc(&c->density, c->N * sizeof(float)));
-    CKD(cudaMalloc(&c->mask, c->N));
+    CKD(cudaMalloc(&c->density, NB * sizeof(float)));
+    CKD(cudaMalloc(&c->nzbits, c->N / 8));
+    CKD(cudaMalloc(&c->maskbits, c->N / 8));
     CKD(cudaMalloc(&c->P2, NB * sizeof(double2)));
     CKD(cudaMalloc(&c->PXX, NB * sizeof(double)));
     (void)NW;
@@ -249,8 +252,11 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->up_alloc, c->band_words * sizeof(short)));
     CKD(cudaMalloc(&c->dn_alloc, c->band_words * sizeof(short)));
     c->up = c->up_alloc - woff; c->dn = c->dn_alloc - woff;
-    CKD(cudaMalloc(&c->rle, NB * sizeof(int2)));
+    c->rle_cap = c->g.nrows() * std::min(n, srm_band_bufcap(n));   // enough for every row at the band kernel's capacity
+    CKD(cudaMalloc(&c->rle, (size_t)c->rle_cap * sizeof(int2)));
+    CKD(cudaMalloc(&c->row_scratch, (size_t)srm_row_scratch_ctas(c->g.nrows()) * n * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
+    CKD(cudaMalloc(&c->rle_off, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
     CKD(cudaMalloc(&c->flags, 64 * sizeof(int)));
@@ -275,8 +281,8 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->flags) cudaFree(c->flags);
     if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
     if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
-    void *ptrs[] = {c->density, c->mask, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
-                    c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->rle_cnt, c->ovf_rows,
+    void *ptrs[] = {c->density, c->nzbits, c->maskbits, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
+                    c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->row_scratch, c->rle_cnt, c->rle_off, c->ovf_rows,
                     c->edge[0], c->edge[1], c->hash[0].b, c->hash[1].b, c->labels, c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -421,7 +427,8 @@ extern "C" int srm_synchronize(srm_ctx *c) {
 
 // pbaCVDComputeWeightedPrefix (gcvt.cu:995-1006), fp64, rows of this band only; c->density is already filled.
 static int density_ready(srm_ctx *c) {
-    srm_launch_prefix(c->stream, c->density + (size_t)c->g.row0 * c->g.n, c->g, c->P2, c->PXX);
+    srm_launch_prefix(c->stream, c->density, c->g, c->P2, c->PXX);
+    if (!is_band(c)) srm_launch_nonzero_bits_f32(c->stream, c->density, c->N, c->nzbits);   // (bands: see srm_set_density*)
     CK(cudaGetLastError());
     c->has_density = true;
     return SRM_OK;
@@ -449,19 +456,63 @@ static int upload(srm_ctx *c, void *dst, const void *src, size_t bytes, int on_d
 extern "C" int srm_set_density(srm_ctx *c, const float *density, int on_device) {
     if (!c || !density) return fail(SRM_ERR_ARG, "srm_set_density: null argument");
     CK(cudaSetDevice(c->device));
-    int rc = upload(c, c->density, density, c->N * sizeof(float), on_device);
+    const int n = c->g.n, r0 = c->g.row0, r1 = c->g.row1;
+    const size_t NB = (size_t)(r1 - r0) * n;
+    int rc = upload(c, c->density, density + (size_t)r0 * n, NB * sizeof(float), on_device);
     if (rc) return rc;
+    if (!is_band(c)) {
+        // whole grid: density_ready() derives the bitmap from c->density
+    } else if (on_device) {
+        srm_launch_nonzero_bits_f32(c->stream, density, c->N, c->nzbits);   // straight from the caller's device array
+    } else {
+        // row band, full-grid host array: the band's rows stay on the device; the other rows only pass through a scratch
+        // buffer for their "non-zero" bits.  (srm_set_density_band + an exchange of the bitmap slices avoids this.)
+        srm_launch_nonzero_bits_f32(c->stream, c->density, NB, c->nzbits + (size_t)r0 * n / 32);
+        float *tmp = nullptr;
+        CK(cudaMalloc(&tmp, (size_t)64 * n * sizeof(float)));
+        for (int b = 0; b < n && rc == SRM_OK; b += 64) {   // band boundaries are multiples of 64 rows
+            if (b >= r0 && b < r1) continue;
+            rc = upload(c, tmp, density + (size_t)b * n, (size_t)64 * n * sizeof(float), 0);
+            if (rc == SRM_OK) srm_launch_nonzero_bits_f32(c->stream, tmp, (size_t)64 * n, c->nzbits + (size_t)b * n / 32);
+            if (rc == SRM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SRM_ERR_CUDA, "srm_set_density: sync failed");
+        }
+        cudaFree(tmp);
+        if (rc) return rc;
+    }
+    CK(cudaGetLastError());
     return density_ready(c);
+}
+
+// Row bands: only the band's own rows ((row1 - row0) * n floats).  The "density != 0" bits of the OTHER rows must then be
+// supplied by the caller: every rank fills its slice, the slices are exchanged through srm_shared_bits (all-gather).
+extern "C" int srm_set_density_band(srm_ctx *c, const float *band_rows, int on_device) {
+    if (!c || !band_rows) return fail(SRM_ERR_ARG, "srm_set_density_band: null argument");
+    CK(cudaSetDevice(c->device));
+    const size_t NB = (size_t)c->g.nrows() * c->g.n;
+    int rc = upload(c, c->density, band_rows, NB * sizeof(float), on_device);
+    if (rc) return rc;
+    srm_launch_nonzero_bits_f32(c->stream, c->density, NB, c->nzbits + (size_t)c->g.row0 * c->g.n / 32);
+    CK(cudaGetLastError());
+    return density_ready(c);
+}
+
+// Device pointers of the two full-grid bitmaps (which = 0: density != 0, 1: constraint pixels): n*n/32 words, row y
+// starts at word y*n/32.  For the exchange of the band slices between ranks.
+extern "C" int srm_shared_bits(srm_ctx *c, int which, void **device_ptr, size_t *num_words) {
+    if (!c || !device_ptr || !num_words || which < 0 || which > 1) return fail(SRM_ERR_ARG, "srm_shared_bits: bad argument");
+    *device_ptr = which ? c->maskbits : c->nzbits;
+    *num_words = c->N / 32;
+    return SRM_OK;
 }
 
 // dense device mask from the list of constraint pixels (packed x | y << 16)
 static int set_mask_pixels(srm_ctx *c, const std::vector<int> &px) {
-    CK(cudaMemsetAsync(c->mask, 0, c->N, c->stream));
+    CK(cudaMemsetAsync(c->maskbits, 0, c->N / 8, c->stream));
     if (!px.empty()) {
         int *d = nullptr;
         CK(cudaMalloc(&d, px.size() * sizeof(int)));
         cudaError_t e = cudaMemcpyAsync(d, px.data(), px.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) { srm_launch_scatter_mask(c->stream, d, (int)px.size(), c->g.n, c->mask); e = cudaGetLastError(); }
+        if (e == cudaSuccess) { srm_launch_scatter_mask(c->stream, d, (int)px.size(), c->g.n, c->maskbits); e = cudaGetLastError(); }
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);   // px may be a local of the caller
         cudaFree(d);
         if (e != cudaSuccess) return fail(SRM_ERR_CUDA, "srm_set_mask: %s", cudaGetErrorString(e));
@@ -475,7 +526,8 @@ extern "C" int srm_set_mask(srm_ctx *c, const unsigned char *mask, int on_device
     CK(cudaSetDevice(c->device));
     if (!mask) { c->has_mask = false; return SRM_OK; }
     if (on_device) {
-        CK(cudaMemcpyAsync(c->mask, mask, c->N, cudaMemcpyDeviceToDevice, c->stream));
+        srm_launch_nonzero_bits_u8(c->stream, mask, c->N, c->maskbits);
+        CK(cudaGetLastError());
         c->has_mask = true;
         return SRM_OK;
     }
@@ -672,6 +724,13 @@ extern "C" int srm_set_omega(srm_ctx *c, float omega) {
 // Inside the loop both agree until a stop; after a stop every kernel is a no-op, so using the
 // host parity for the (skipped) launches is harmless.  For calls outside the loop (final labelling)
 // the parity is read back from the device.
+static SrmRle rle_of(srm_ctx *c) {
+    SrmRle R;
+    R.pool = c->rle; R.off = c->rle_off; R.cnt = c->rle_cnt; R.cap = c->rle_cap;
+    R.scratch = c->row_scratch; R.scratch_ctas = srm_row_scratch_ctas(c->g.nrows());
+    return R;
+}
+
 static int band_flags(srm_ctx *c, int respect_stop, int accumulate, int want_energy, int write_rle) {
     return (accumulate ? SRM_BF_ACC : 0) | (want_energy ? SRM_BF_ENERGY : 0) | (respect_stop ? SRM_BF_STOP : 0) |
            (write_rle ? SRM_BF_RLE : 0) | (c->p2p ? SRM_BF_TOUCH : 0);
@@ -684,14 +743,14 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
     srm_launch_carry(c->stream, s, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1);
     const int *rows = nullptr, *count = nullptr;
     if (!c->robust_only) {
-        CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+        CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), c->ovf_rows, c->P2, c->PXX,
                            s.hash, acc, c->Kcap, c->ctl, band_flags(c, respect_stop, accumulate, want_energy, write_rle),
                            c->dbg_stats));
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
-    CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, s.hash,
-                      acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop));
+    CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), rows, count, c->P2, c->PXX, s.hash,
+                      acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, write_rle));
     if (accumulate) srm_launch_signal(c->stream, c->ctl, peers_of(c, it), respect_stop);
     return SRM_OK;
 }
@@ -703,11 +762,37 @@ static int require_ready(srm_ctx *c, const char *who, bool need_density) {
     return SRM_OK;
 }
 
+// After a labelling that wrote run-length rows: if a row found the pool exhausted (more runs per row on average than
+// the band kernel's buffer holds: adversarial site sets only), grow the pool to the worst case (one run per pixel) and
+// label again.  Synchronises the stream.
+static int ensure_rle(srm_ctx *c) {
+    CK(cudaStreamSynchronize(c->stream));
+    int failed = 0;
+    CK(cudaMemcpy(&failed, &c->ctl->rle_fail, sizeof(int), cudaMemcpyDeviceToHost));
+    if (!failed) return SRM_OK;
+    const size_t full = (size_t)c->g.nrows() * c->g.n;
+    if ((size_t)c->rle_cap >= full) return fail(SRM_ERR_STATE, "run-length pool exhausted at its full size");
+    cudaFree(c->rle);
+    c->rle = nullptr;
+    CK(cudaMalloc(&c->rle, full * sizeof(int2)));
+    c->rle_cap = (int)full;
+    failed = 0;
+    CK(cudaMemcpy(&c->ctl->rle_fail, &failed, sizeof(int), cudaMemcpyHostToDevice));
+    int rc = label_with(c, c->it_host, 0, 0, 0);   // labels only: the sums of the first pass are complete
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&failed, &c->ctl->rle_fail, sizeof(int), cudaMemcpyDeviceToHost));
+    if (failed) return fail(SRM_ERR_STATE, "run-length pool exhausted at its full size");
+    return SRM_OK;
+}
+
 extern "C" int srm_label(srm_ctx *c) {
     int rc = require_ready(c, "srm_label", false);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
     rc = label_with(c, c->it_host, 0, 0, 0);
+    if (rc) return rc;
+    rc = ensure_rle(c);
     if (rc) return rc;
     c->labelled = true;
     return SRM_OK;
@@ -721,6 +806,8 @@ extern "C" int srm_label_accumulate(srm_ctx *c, int want_energy) {
     CK(cudaSetDevice(c->device));
     rc = label_with(c, c->it_host, 0, 1, want_energy);
     if (rc) return rc;
+    rc = ensure_rle(c);
+    if (rc) return rc;
     c->labelled = true;
     return SRM_OK;
 }
@@ -730,7 +817,7 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     if (rc) return rc;
     if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
     CK(cudaSetDevice(c->device));
-    srm_launch_acc(c->stream, c->rle, c->rle_cnt, c->P2, c->PXX, c->hash[c->it_host & 1], c->g, cur_acc(c, c->it_host), c->Kcap,
+    srm_launch_acc(c->stream, rle_of(c), c->P2, c->PXX, c->hash[c->it_host & 1], c->g, cur_acc(c, c->it_host), c->Kcap,
                    nullptr, nullptr, c->ctl, want_energy, 0);
     srm_launch_signal(c->stream, c->ctl, peers_of(c, c->it_host), 0);
     CK(cudaGetLastError());
@@ -755,7 +842,7 @@ extern "C" int srm_update(srm_ctx *c) {
     // (stepwise mode with world > 1 and no bound collective is the caller-side all-reduce of ShardedLloyd.step:
     //  srm_acc_buffer hands out the sums, so nothing to check here)
     const int buf = current_buffer(c);
-    srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density, c->has_mask ? c->mask : nullptr,
+    srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->nzbits, c->has_mask ? c->maskbits : nullptr,
                       c->g, c->ctl, c->Kcap, c->newpos, step_of(c, c->it_host), (c->it_host % 10) == 0, 0, 0,
                       peers_of(c, c->it_host));
     CK(cudaGetLastError());
@@ -778,8 +865,8 @@ extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
         if (rc) return rc;
         rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
         if (rc) return rc;
-        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g, c->ctl, c->Kcap, c->newpos, step_of(c, it), want_energy,
+        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->nzbits,
+                          c->has_mask ? c->maskbits : nullptr, c->g, c->ctl, c->Kcap, c->newpos, step_of(c, it), want_energy,
                           stop_rule, 1, peers_of(c, it));
     }
     CK(cudaGetLastError());
@@ -818,21 +905,21 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         CK(cudaEventRecord(e[1], c->stream));
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {
-            CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, c->ovf_rows, c->P2, c->PXX,
+            CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), c->ovf_rows, c->P2, c->PXX,
                                s.hash, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats));
             rows = c->ovf_rows;
             count = &c->ctl->ovf;
         }
         CK(cudaEventRecord(e[2], c->stream));
-        CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, c->rle, c->rle_cnt, rows, count, c->P2, c->PXX, s.hash,
-                          acc, c->Kcap, c->ctl, 1, want_energy, 1));
+        CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), rows, count, c->P2, c->PXX, s.hash,
+                          acc, c->Kcap, c->ctl, 1, want_energy, 1, 0));
         CK(cudaEventRecord(e[3], c->stream));
         srm_launch_signal(c->stream, c->ctl, peers_of(c, it), 1);
         rc = allreduce_acc(c);
         if (rc) return rc;
         CK(cudaEventRecord(e[4], c->stream));
-        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->density,
-                          c->has_mask ? c->mask : nullptr, c->g, c->ctl, c->Kcap, c->newpos, s, want_energy,
+        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->nzbits,
+                          c->has_mask ? c->maskbits : nullptr, c->g, c->ctl, c->Kcap, c->newpos, s, want_energy,
                           stop_rule, 1, peers_of(c, it));
         CK(cudaEventRecord(e[5], c->stream));
     }
@@ -901,7 +988,7 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
         if (!c->labels) CK(cudaMalloc(&c->labels, NB * sizeof(int)));
         dst = c->labels;
     }
-    CK(srm_launch_expand(c->stream, c->rle, c->rle_cnt, c->g, dst));
+    CK(srm_launch_expand(c->stream, rle_of(c), c->g, dst));
     if (!on_device) {
         if (host_ptr_is_pinned(out)) CK(cudaMemcpyAsync(out, dst, NB * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         else CK(srm_d2h_pageable(out, dst, NB * sizeof(int), c->stream));

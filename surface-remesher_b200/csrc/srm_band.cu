@@ -270,7 +270,7 @@ __device__ __forceinline__ void cp_async_wait_pending(int pending) {   // warp-u
 template <int RPW, int C>
 __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *__restrict__ bits, const short *__restrict__ up,
                                                   const short *__restrict__ dn, int n, int row0, int CL,
-                                                  int2 *__restrict__ rle, int *__restrict__ rle_cnt, int *ovf_rows,
+                                                  SrmRle rle, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                   SrmHash hash, double *__restrict__ acc, int Kcap,
                                                   SrmCtl *ctl, int flags, int dbg) {
@@ -477,10 +477,13 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 if (!removed) break;
             }
         }
-        if (lane == 0) rle_cnt[r] = m;
+        if (!(flags & SRM_BF_RLE) && lane == 0) rle.cnt[r] = m;   // statistics only (srm_debug_counts)
         if (flags & SRM_BF_RLE) {
-            // runs -> global run-length row (final labelling and the stepwise API; nothing in the loop reads it)
-            int2 *out = rle + (size_t)r * n;
+            // runs -> run-length pool (final labelling and the stepwise API; nothing in the loop reads it)
+            int po = 0;
+            if (lane == 0) po = srm_rle_alloc(rle, ctl, r, m);
+            po = __shfl_sync(0xffffffffu, po, 0);
+            int2 *out = rle.pool + max(po, 0);
             int carryB = -1;
             for (int base = 0; base < m; base += 62) {
 #pragma unroll
@@ -490,7 +493,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                     const unsigned v = valid ? (buf[e] & 0x7fffffffu) : 0u;
                     const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
                     const RoundStep st = round_step(valid, e + 1 < m, v, x, x * x + g * g, Y, lane, n, carryB);
-                    if (st.owned) out[e] = make_int2((int)v, st.Bc + 1);
+                    if (st.owned && po >= 0) out[e] = make_int2((int)v, st.Bc + 1);
                 }
             }
         }
@@ -632,20 +635,22 @@ static int band_rpw(int nrows) {
 
 template <int RPW, int C>
 static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, const short *up, const short *dn, SrmGrid g,
-                            int CL, int2 *rle, int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX,
+                            int CL, SrmRle rle, int *ovf_rows, const double2 *P2, const double *PXX,
                             SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int nbands = g.nrows() / (BAND_NW * RPW);
-    srm_launch_pdl(st, dim3(nbands), dim3(BAND_NT), smem, k_band<RPW, C>, bits, up, dn, g.n, g.row0, CL, rle, rle_cnt, ovf_rows, P2,
+    srm_launch_pdl(st, dim3(nbands), dim3(BAND_NT), smem, k_band<RPW, C>, bits, up, dn, g.n, g.row0, CL, rle, ovf_rows, P2,
                    PXX, hash, acc, Kcap, ctl, flags, dbg);
 }
 
-cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
+int srm_band_bufcap(int n) { return band_bufcap(n); }
+
+cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
+                            int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
                             double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
     const int CL = band_cap(g.n);
     const size_t smem = band_smem(g.n, CL);
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
-#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, rle_cnt, ovf_rows, P2, PXX, hash, acc, Kcap, ctl, flags, dbg
+#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, ovf_rows, P2, PXX, hash, acc, Kcap, ctl, flags, dbg
     if (C == BAND_C8K) { if (rpw == 1) band_launch_one<1, BAND_C8K>(BAND_ARGS); else band_launch_one<2, BAND_C8K>(BAND_ARGS); }
     else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
     else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }

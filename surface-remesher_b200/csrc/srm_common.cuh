@@ -24,6 +24,8 @@ struct SrmCtl {
     int band_ticket; // next band of the persistent band kernel (reset with ovf by k_bits)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
+    int rle_used;    // entries of the run-length pool handed out by the current labelling (reset by the carry kernel)
+    int rle_fail;    // a row found the pool exhausted (its offset is -1): the host grows the pool and labels again
     float escale;    // multires: energy factor 4^level (gcvt.cu:1082); 1 on the finest level
     double thresh;   // stopping threshold on the energy gradient: 1e-5 finest, 3e-1 coarse levels (gcvt.cu:1132-1137)
     int dbg[8];     // optional statistics of the band kernel: max/sum of band-list and row-survivor sizes
@@ -155,6 +157,26 @@ static inline cudaError_t srm_launch_pdl(cudaStream_t st, dim3 grid, dim3 block,
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// Run-length labels of a labelling: row r holds cnt[r] runs {packed site, first X} at pool[off[r]..].  Rows allocate
+// exactly what they need from one pool (atomicAdd on SrmCtl::rle_used); the pool has rows * min(n, buffer capacity)
+// entries instead of rows * n (537 MB at 8192^2 in round 1), and a labelling that exhausts it (adversarial inputs only:
+// more runs per row than the band kernel's buffer on average) is repeated by the host with a full-size pool.
+struct SrmRle {
+    int2 *pool = nullptr;
+    int *off = nullptr, *cnt = nullptr;
+    int cap = 0;
+    int2 *scratch = nullptr;   // robust row kernel: n entries per CTA (it accumulates from here, pool or not)
+    int scratch_ctas = 0;
+};
+__device__ __forceinline__ int srm_rle_alloc(const SrmRle &R, SrmCtl *ctl, int r, int count) {   // one thread per row
+    const int o = atomicAdd(&ctl->rle_used, count);
+    const bool ok = o + count <= R.cap;
+    R.off[r] = ok ? o : -1;
+    R.cnt[r] = count;
+    if (!ok) atomicExch(&ctl->rle_fail, 1);
+    return ok ? o : -1;
+}
+
 // ---- launchers (host), one per pipeline stage; all asynchronous on `st`.
 struct SrmGrid {           // geometry of one context
     int n, row0, row1;
@@ -180,6 +202,7 @@ void srm_launch_carry(cudaStream_t st, const SrmStep &s, int n, short *up, short
                       int row0, int row1);
 // fused fast path (srm_band.cu)
 cudaError_t srm_band_setup(int n);
+int srm_band_bufcap(int n);   // entries of a warp's element buffer = most runs a band-kernel row can have
 // flags of the band kernel
 enum {
     SRM_BF_ACC = 1,      // accumulate the per-site sums (fused centroid pass)
@@ -188,25 +211,29 @@ enum {
     SRM_BF_RLE = 8,      // write the run-length rows (final labelling, stepwise API; the loop does not need them)
     SRM_BF_TOUCH = 16    // mark the sites this rank contributed to (read by the peer-memory all-reduce)
 };
-cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                            int *rle_cnt, int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
+cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
+                            int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
                             double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg = 0);
 // robust path, driven by a row list (rows == nullptr: every row of the band)
-cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                           int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
-                           SrmHash hash, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
-                           int respect_stop);
-cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels);
+cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
+                           const int *rows, const int *count, const double2 *P2, const double *PXX,
+                           SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
+                           int respect_stop, int write_rle);
+int srm_row_scratch_ctas(int nrows);   // CTAs of the robust row kernel (= n-entry slices of SrmRle::scratch)
+cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels);
 cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes
 
 void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX);
-void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
+void srm_launch_acc(cudaStream_t st, SrmRle rle, const double2 *P2, const double *PXX,
                     SrmHash hash, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
                     const SrmCtl *ctl, int want_energy, int respect_stop);
 // Site update (two kernels): new positions + claims in s.hash_next, then winners -> sites_out / s.bits_next / s.edge_next.
-void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
+void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const uint32_t *nzbits,
+                       const uint32_t *maskbits, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
                        int want_energy, int stop_rule, int respect_stop, SrmPeers peers = SrmPeers());
+// one bit per value: "value != 0"; count must be a multiple of 32
+void srm_launch_nonzero_bits_f32(cudaStream_t st, const float *v, size_t count, uint32_t *out);
+void srm_launch_nonzero_bits_u8(cudaStream_t st, const unsigned char *v, size_t count, uint32_t *out);
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop);
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
                                int *blockoff, int *total_out, int count_only);
@@ -239,5 +266,5 @@ cudaError_t srm_d2h_pageable(void *dst_host, const void *src_dev, size_t bytes, 
 void srm_scan_site_map(const int *site_map, size_t N, std::vector<int> &sites);
 void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels);
 void srm_host_pool_release();
-void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, unsigned char *mask);
+void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, uint32_t *maskbits);
 #endif

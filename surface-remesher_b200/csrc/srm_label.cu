@@ -16,6 +16,7 @@
 // row tie -> smallest x: gcvt.cu:449-466).
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------ sites -> bitmap
 
@@ -74,7 +75,7 @@ __device__ __forceinline__ int edge_bot(const int *edge, int n, int x) {
 // iteration): it zeroes the bitmap words at the indices it scans, and clears the hash table, the band edges and the
 // robust-path row counter grid-wide.  This replaces the per-iteration memsets and the k_bits kernel of round 1.
 __device__ __forceinline__ void carry_clear_next(const SrmStep &s, int n, SrmCtl *ctl, size_t tid, size_t nthreads) {
-    if (tid == 0) ctl->ovf = 0;
+    if (tid == 0) { ctl->ovf = 0; ctl->rle_used = 0; }
     const uint4 e = make_uint4(SRM_HEMPTY, 0xffffffffu, SRM_HEMPTY, 0xffffffffu);
     for (size_t i = tid; i <= (size_t)s.hash_next.mask; i += nthreads) s.hash_next.b[i] = e;
     if (s.edge_next)
@@ -271,16 +272,17 @@ __device__ __forceinline__ int cand8_dist(const uint32_t *__restrict__ bits, con
 // block (sound: DESIGN.md §row pass), compact the survivors.  P2: per-thread stacks over short
 // segments + log2(128) bridging levels.  P3: compact the envelope to global.
 __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bits, const short *__restrict__ up,
-                                                const short *__restrict__ dn, int n, int row0, int nrows, int2 *rle,
-                                                int *__restrict__ rle_cnt, const int *__restrict__ rows,
+                                                const short *__restrict__ dn, int n, int row0, int nrows, SrmRle R,
+                                                const int *__restrict__ rows,
                                                 const int *__restrict__ count, const double2 *__restrict__ P2,
                                                 const double *__restrict__ PXX, SrmHash hash,
-                                                double *__restrict__ acc, int Kcap, const SrmCtl *__restrict__ ctl,
-                                                int accumulate, int want_energy, int respect_stop) {
+                                                double *__restrict__ acc, int Kcap, SrmCtl *ctl,
+                                                int accumulate, int want_energy, int respect_stop, int write_rle) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
     __shared__ int row_total;   // runs of the row (its own word: wtot[] is still being read by slower warps)
+    __shared__ int pool_off;
     srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
     EnvSmem s;
@@ -350,7 +352,9 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
             __syncthreads();
         }
 
-        // P3: compact to global run-length form
+        // P3: compact to run-length form in this CTA's scratch row (the accumulation reads it from there), then — if the
+        // labels are wanted — into the pool
+        int2 *mine = R.scratch + (size_t)blockIdx.x * n;
         {
             const int b = s.sb[t], e = s.se[t], cnt = e - b;
             int incl = warp_incl_scan(cnt, lane);
@@ -358,13 +362,19 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
             __syncthreads();
             int off = incl - cnt;
             for (int k = 0; k < w; ++k) off += wtot[k];
-            int2 *out = rle + (size_t)r * n + off;
+            int2 *out = mine + off;
             for (int i = b; i < e; ++i) out[i - b] = make_int2(srm_pack(s.x[i], s.c[i]), (int)s.S[i] + 1);
-            if (t == ROW_NT - 1) { rle_cnt[r] = off + cnt; row_total = off + cnt; }
+            if (t == ROW_NT - 1) {
+                row_total = off + cnt;
+                pool_off = write_rle ? srm_rle_alloc(R, ctl, r, off + cnt) : -1;
+                if (!write_rle) R.cnt[r] = off + cnt;
+            }
         }
         __syncthreads();
+        if (pool_off >= 0)
+            for (int i = t; i < row_total; i += ROW_NT) R.pool[pool_off + i] = mine[i];
         if (accumulate && w == 0) {
-            double e_loc = acc_row(rle + (size_t)r * n, row_total, P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, Y, acc,
+            double e_loc = acc_row(mine, row_total, P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, Y, acc,
                                    Kcap, want_energy, lane);
             if (want_energy) {
                 e_loc = warp_sum(e_loc);
@@ -377,7 +387,7 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
 
 static size_t row_smem_bytes(int n) { return (size_t)n * 6; }  // 192 KB at n = 32768
 
-__global__ void k_expand(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt, int n, int *__restrict__ labels);
+__global__ void k_expand(SrmRle R, int n, int *__restrict__ labels);
 
 cudaError_t srm_label_setup(int n) {
     // per function, not per context: opt in for the largest grid (contexts of different sizes coexist)
@@ -388,13 +398,16 @@ cudaError_t srm_label_setup(int n) {
     return srm_band_setup(n);
 }
 
-cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, int2 *rle,
-                           int *rle_cnt, const int *rows, const int *count, const double2 *P2, const double *PXX,
-                           SrmHash hash, double *acc, int Kcap, const SrmCtl *ctl, int accumulate, int want_energy,
-                           int respect_stop) {
-    const int grid = rows ? 148 : g.nrows();
-    srm_launch_pdl(st, dim3(grid), dim3(ROW_NT), row_smem_bytes(g.n), k_row, bits, up, dn, g.n, g.row0, g.nrows(), rle, rle_cnt, rows,
-                   count, P2, PXX, hash, acc, Kcap, ctl, accumulate, want_energy, respect_stop);
+int srm_row_scratch_ctas(int nrows) { (void)nrows; return 148; }
+
+cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
+                           const int *rows, const int *count, const double2 *P2, const double *PXX,
+                           SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
+                           int respect_stop, int write_rle) {
+    // rows == nullptr: every row of the band (CTAs loop over the rows); else the listed rows
+    const int grid = rows ? 148 : std::min(g.nrows(), rle.scratch_ctas);
+    srm_launch_pdl(st, dim3(grid), dim3(ROW_NT), row_smem_bytes(g.n), k_row, bits, up, dn, g.n, g.row0, g.nrows(), rle, rows,
+                   count, P2, PXX, hash, acc, Kcap, ctl, accumulate, want_energy, respect_stop, write_rle);
     return cudaGetLastError();
 }
 
@@ -402,13 +415,13 @@ cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *u
 
 #define EXP_NT 256
 // One CTA per row: scatter the run heads into a shared row, then a "last valid value" scan.
-__global__ void __launch_bounds__(EXP_NT) k_expand(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt, int n,
-                                                   int *__restrict__ labels) {
+__global__ void __launch_bounds__(EXP_NT) k_expand(SrmRle R, int n, int *__restrict__ labels) {
     extern __shared__ __align__(16) int buf[];
     __shared__ int wlast[EXP_NT / 32];
     const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int cnt = rle_cnt[r];
-    const int2 *rr = rle + (size_t)r * n;
+    if (R.off[r] < 0) return;   // the pool was exhausted: the host repeats the labelling with a larger one
+    const int cnt = R.cnt[r];
+    const int2 *rr = R.pool + R.off[r];
     for (int i = t; i < n; i += EXP_NT) buf[i] = SRM_SENT;
     __syncthreads();
     for (int e = t; e < cnt; e += EXP_NT) { int2 v = rr[e]; buf[v.y] = v.x; }
@@ -443,9 +456,9 @@ __global__ void __launch_bounds__(EXP_NT) k_expand(const int2 *__restrict__ rle,
     }
 }
 
-cudaError_t srm_launch_expand(cudaStream_t st, const int2 *rle, const int *rle_cnt, SrmGrid g, int *labels) {
+cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels) {
     size_t sm = (size_t)g.n * sizeof(int);
-    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, rle_cnt, g.n, labels);
+    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, g.n, labels);
     return cudaGetLastError();
 }
 

@@ -11,6 +11,7 @@
 // (W, X, Y, pad) and are all-reduced across row bands by the caller when sharded.
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
+#include <algorithm>
 
 // ------------------------------------------------------------------ prefix sums (once per call)
 
@@ -71,7 +72,7 @@ void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, do
 
 #define ACC_NT 128
 // Robust-path accumulation: one warp per listed row (rows == nullptr: all rows of the band).
-__global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, const int *__restrict__ rle_cnt,
+__global__ void __launch_bounds__(ACC_NT) k_acc(SrmRle R,
                                                 const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                 SrmHash hash, int n, int row0, int nrows,
                                                 double *__restrict__ acc, int Kcap, const int *__restrict__ rows,
@@ -84,7 +85,8 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
     double e_loc = 0;
     for (int q = blockIdx.x * (ACC_NT / 32) + (threadIdx.x >> 5); q < total; q += nwarps) {
         const int r = rows ? rows[q] : q;
-        e_loc += acc_row(rle + (size_t)r * n, rle_cnt[r], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, row0 + r, acc,
+        if (R.off[r] < 0) continue;   // pool exhausted for this row (flagged in SrmCtl::rle_fail)
+        e_loc += acc_row(R.pool + R.off[r], R.cnt[r], P2 + srm_pfx_row(r, n), PXX + srm_pfx_row(r, n), hash, n, row0 + r, acc,
                          Kcap, want_energy, lane);
     }
     if (want_energy) {
@@ -93,12 +95,12 @@ __global__ void __launch_bounds__(ACC_NT) k_acc(const int2 *__restrict__ rle, co
     }
 }
 
-void srm_launch_acc(cudaStream_t st, const int2 *rle, const int *rle_cnt, const double2 *P2, const double *PXX,
+void srm_launch_acc(cudaStream_t st, SrmRle rle, const double2 *P2, const double *PXX,
                     SrmHash hash, SrmGrid g, double *acc, int Kcap, const int *rows, const int *count,
                     const SrmCtl *ctl, int want_energy, int respect_stop) {
     const int rows_per_block = ACC_NT / 32;
     const int grid = rows ? 148 : (g.nrows() + rows_per_block - 1) / rows_per_block;
-    SRM_COUNT(), k_acc<<<grid, ACC_NT, 0, st>>>(rle, rle_cnt, P2, PXX, hash, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
+    SRM_COUNT(), k_acc<<<grid, ACC_NT, 0, st>>>(rle, P2, PXX, hash, g.n, g.row0, g.nrows(), acc, Kcap, rows, count, ctl,
                                    want_energy, respect_stop);
 }
 
@@ -163,8 +165,13 @@ void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect
     if (peers.world > 1) srm_launch_pdl(st, dim3(1), dim3(32), 0, k_signal, ctl, peers, respect_stop);
 }
 
-__global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const float *__restrict__ density,
-                             const unsigned char *__restrict__ mask, int n, SrmCtl *ctl, int *__restrict__ newpos,
+// nzbits / maskbits: one bit per pixel, word (y * n + x) >> 5, bit x & 31: "density != 0" (gcvt.cu:777) and "constraint
+// pixel" (gcvt.cu:776).  Full-grid bitmaps of N/8 bytes each replace the replicated 4 B/px density and 1 B/px mask of
+// round 1: the update is replicated on every rank and may look at any pixel.
+__device__ __forceinline__ bool srm_bit(const uint32_t *__restrict__ b, size_t i) { return (b[i >> 5] >> (i & 31)) & 1u; }
+
+__global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const uint32_t *__restrict__ nzbits,
+                             const uint32_t *__restrict__ maskbits, int n, SrmCtl *ctl, int *__restrict__ newpos,
                              SrmHash claim, int respect_stop, SrmPeers peers) {
     srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
@@ -190,7 +197,7 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
     if (p == SRM_SENT) { newpos[id] = SRM_SENT; return; }
     const int tx = srm_x(p), ty = srm_y(p);
     int rx = tx, ry = ty;
-    if (!(mask && mask[(size_t)ty * n + tx])) {
+    if (!(maskbits && srm_bit(maskbits, (size_t)ty * n + tx))) {
         double sW = 0, sX = 0, sY = 0;
         if (peers.world > 1) {
             // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
@@ -235,7 +242,7 @@ __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, c
         int cx = __float2int_rz(fx), cy = __float2int_rz(fy);  // NaN -> 0, like F2I.TRUNC
         cx = max(min(cx, n - 1), 0);
         cy = max(min(cy, n - 1), 0);
-        if (density[(size_t)cy * n + cx] != 0.0f) { rx = cx; ry = cy; }
+        if (srm_bit(nzbits, (size_t)cy * n + cx)) { rx = cx; ry = cy; }
     }
     const int np = srm_pack(rx, ry);
     newpos[id] = np;
@@ -319,13 +326,13 @@ __global__ void __launch_bounds__(UPD_NT) k_update_resolve(const int *__restrict
     }
 }
 
-void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const float *density,
-                       const unsigned char *mask, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
+void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, double *acc, const uint32_t *nzbits,
+                       const uint32_t *maskbits, SrmGrid g, SrmCtl *ctl, int Kcap, int *newpos, const SrmStep &s,
                        int want_energy, int stop_rule, int respect_stop, SrmPeers peers) {
     // acc: single GPU: the accumulator buffer; peers: the BASE of this rank's buffer pair
     const int k1 = Kcap > 0 ? Kcap : 1;
-    srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, density, mask, g.n, ctl, newpos,
-                   s.hash_next, respect_stop, peers);
+    srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, nzbits, maskbits, g.n, ctl,
+                   newpos, s.hash_next, respect_stop, peers);
     srm_launch_pdl(st, dim3((k1 + UPD_NT - 1) / UPD_NT), dim3(UPD_NT), 0, k_update_resolve, (const int *)newpos, s.hash_next, g.n, g.row0,
                    g.row1, s.bits_next, s.edge_next, ctl, sites_out, acc, Kcap, want_energy, stop_rule, respect_stop, peers);
 }
@@ -362,16 +369,47 @@ void srm_launch_zoom_sites(cudaStream_t st, const int *in, int *out, int K) {
     if (K > 0) SRM_COUNT(), k_zoom_sites<<<(K + 255) / 256, 256, 0, st>>>(in, out, K);
 }
 
-// constraint pixels found by the host scan (srm_host.cu) -> dense 1 B/px mask (cleared by the caller)
-__global__ void k_scatter_mask(const int *__restrict__ pixels, int count, int n, unsigned char *__restrict__ mask) {
+// constraint pixels found by the host scan (srm_host.cu) -> mask bitmap (cleared by the caller)
+__global__ void k_scatter_mask(const int *__restrict__ pixels, int count, int n, uint32_t *__restrict__ maskbits) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     const int p = pixels[i];
-    mask[(size_t)srm_y(p) * n + srm_x(p)] = 1;
+    const size_t px = (size_t)srm_y(p) * n + srm_x(p);
+    atomicOr(&maskbits[px >> 5], 1u << (px & 31));
 }
 
-void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, unsigned char *mask) {
-    if (count > 0) SRM_COUNT(), k_scatter_mask<<<(count + 255) / 256, 256, 0, st>>>(pixels, count, n, mask);
+void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, uint32_t *maskbits) {
+    if (count > 0) SRM_COUNT(), k_scatter_mask<<<(count + 255) / 256, 256, 0, st>>>(pixels, count, n, maskbits);
+}
+
+// 32 consecutive values -> one bitmap word ("value != 0"); one warp per 32 words: lane l reads float / byte l of every
+// group (coalesced) and the ballot is the word.
+template <typename T>
+__global__ void __launch_bounds__(256) k_nonzero_bits(const T *__restrict__ v, size_t words, uint32_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * 256 + threadIdx.x) >> 5, nwarps = ((size_t)gridDim.x * 256) >> 5;
+    for (size_t w0 = warp * 32; w0 < words; w0 += nwarps * 32) {
+        uint32_t mine = 0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const size_t w = w0 + k;
+            const bool nz = w < words && v[w * 32 + lane] != (T)0;
+            const uint32_t b = __ballot_sync(0xffffffffu, nz);
+            if (lane == k) mine = b;
+        }
+        if (w0 + lane < words) out[w0 + lane] = mine;
+    }
+}
+
+void srm_launch_nonzero_bits_f32(cudaStream_t st, const float *v, size_t count, uint32_t *out) {
+    const size_t words = count / 32;
+    const unsigned blocks = (unsigned)std::min<size_t>((words + 255) / 256, 148 * 8);
+    if (words) SRM_COUNT(), k_nonzero_bits<float><<<blocks, 256, 0, st>>>(v, words, out);
+}
+void srm_launch_nonzero_bits_u8(cudaStream_t st, const unsigned char *v, size_t count, uint32_t *out) {
+    const size_t words = count / 32;
+    const unsigned blocks = (unsigned)std::min<size_t>((words + 255) / 256, 148 * 8);
+    if (words) SRM_COUNT(), k_nonzero_bits<unsigned char><<<blocks, 256, 0, st>>>(v, words, out);
 }
 
 // ------------------------------------------------------------------ dense seed map -> site list

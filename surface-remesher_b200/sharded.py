@@ -17,10 +17,10 @@ from .api import Context, row_bands
 
 
 class _CudaArray:
-    """__cuda_array_interface__ view of a raw device pointer (float64 vector)."""
+    """__cuda_array_interface__ view of a raw device pointer (float64 vector by default)."""
 
-    def __init__(self, ptr, count):
-        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr, count, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 3, "strides": None}
 
 
@@ -38,6 +38,25 @@ class CudaBandEngine:
 
     def set_inputs(self, density, mask, site_map):
         self.ctx.set_density(density)
+        self.ctx.set_mask(mask)
+        self.ctx.set_site_map(site_map)
+        ptr, cnt = self.ctx.acc_buffer()
+        self._keep = _CudaArray(ptr, cnt)
+        self._acc = self.torch.as_tensor(self._keep, device=self.device)
+
+    def set_inputs_sharded(self, density, mask, site_map, dist, bands, rank):
+        """Like set_inputs, but this rank uploads only ITS rows of the density (1/world of the bytes); the "density != 0"
+        bitmap the replicated site update needs for the whole grid is completed by exchanging the bands' slices between
+        the ranks (one broadcast per band over NCCL/NVLink: n*n/8 bytes in total)."""
+        n = self.ctx.n
+        r0, r1 = bands[rank]
+        self.ctx.set_density_band(density[r0:r1])
+        ptr, words = self.ctx.shared_bits(0)
+        self._nzkeep = _CudaArray(ptr, words, "<i4")
+        nz = self.torch.as_tensor(self._nzkeep, device=self.device)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        for q, (a, b) in enumerate(bands):
+            dist.broadcast(nz[a * n // 32: b * n // 32], src=q)
         self.ctx.set_mask(mask)
         self.ctx.set_site_map(site_map)
         ptr, cnt = self.ctx.acc_buffer()
@@ -83,9 +102,21 @@ class ShardedLloyd:
 
     def __init__(self, n, rank, world, engine, dist=None, bands=None):
         self.n, self.rank, self.world = n, rank, world
-        self.row0, self.row1 = (bands or row_bands(n, world))[rank]   # bands: e.g. row_bands_balanced(...)
+        self.bands = list(bands) if bands else row_bands(n, world)    # e.g. row_bands_balanced(...)
+        self.row0, self.row1 = self.bands[rank]
         self.engine = engine
         self.dist = dist
+        self.it = 0
+
+    def set_inputs(self, density, mask, site_map):
+        """Inputs of this rank's band.  With the CUDA engine and world > 1 every rank uploads only its own rows of the
+        density and the ranks exchange the "density != 0" bitmap slices (CudaBandEngine.set_inputs_sharded); otherwise the
+        engine takes the full arrays."""
+        if self.world > 1 and hasattr(self.engine, "set_inputs_sharded"):
+            bands = getattr(self, "bands", None) or row_bands(self.n, self.world)
+            self.engine.set_inputs_sharded(density, mask, site_map, self.dist, bands, self.rank)
+        else:
+            self.engine.set_inputs(density, mask, site_map)
         self.it = 0
 
     def step(self):

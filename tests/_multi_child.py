@@ -35,8 +35,11 @@ def main():
         bands = S.row_bands(n, world)
     r0, r1 = bands[rank]
     eng = CudaBandEngine(n, r0, r1, local)
-    eng.set_inputs(dens, mask, seeds)
     sl = ShardedLloyd(n, rank, world, eng, dist, bands)
+    if mode == "nccl":
+        eng.set_inputs(dens, mask, seeds)     # full arrays on every rank (replicated upload)
+    else:
+        sl.set_inputs(dens, mask, seeds)      # sharded upload: own rows + exchange of the non-zero bitmap slices
     if mode != "py":
         sl.bind_native_collective(mode)
     sl.run(iters)

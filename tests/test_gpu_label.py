@@ -277,3 +277,24 @@ def test_large_grid_whole_context_rows_vs_oracle(n, k):
             bad = (got != exp).any(axis=2)
             assert bad.sum() == 0, f"rows {r0}..: {bad.sum()} mismatching pixels, first at {np.argwhere(bad)[:5]}"
     assert ovf == 0
+
+
+def test_run_length_pool_exhaustion_is_retried():
+    """The run-length pool holds rows * min(n, band buffer) entries.  Two of every three pixels are sites here: 1365 runs
+    per row at n = 2048 (pool sized for 1024 per row), every row on the robust path.  The labelling must notice the
+    exhausted pool, grow it and come out exact."""
+    import surface_remesher_b200 as S
+    n = 2048
+    v = np.full((n, n, 2), I.MARK, np.int16)
+    xs = np.arange(n)
+    keep = (xs % 3) != 2
+    v[:, keep, 0] = xs[keep][None, :]
+    v[:, keep, 1] = np.arange(n)[:, None]
+    with S.Context(n) as c:
+        c.set_site_map(v)
+        c.label()
+        runs, ovf = c.debug_counts()
+        got = c.get_labels()
+    assert runs > n * 1024
+    exp = O.label_exact(v)
+    assert (got != exp).sum() == 0
