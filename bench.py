@@ -414,7 +414,8 @@ def run_c4(args, world, rank, local, dist):
     st = eng.state()
     out = {"workload": workload_name(n, k, nmask), "grid": n, "sites": st["num_sites"], "n_gpus": world, "steps": K, "warmup": W,
            "value": K / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / K, "bands": [b[1] - b[0] for b in bands],
-           "k_band_ms_per_rank": band_ms, "sites_sha1_after": {"steps": W + K + 10, "sha1": sites_sha1(sites)},
+           "k_band_ms_per_rank": band_ms, "stages_ms_per_step_rank0": {s_: round(v / 10, 4) for s_, v in stage.items()},
+           "sites_sha1_after": {"steps": W + K + 10, "sha1": sites_sha1(sites)},
            "setup_s": round(t_setup, 1)}
     eng.close()
     del mask

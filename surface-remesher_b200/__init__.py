@@ -23,8 +23,10 @@ from .api import (  # noqa: F401
     row_bands,
     row_bands_balanced,
 )
+from .batch import BatchLloyd, shard_meshes  # noqa: F401
 
 __all__ = [
     "MARKER", "Context", "SrmError", "centroidalVoronoi", "discretization_d", "gCVT", "generateMask",
     "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands", "row_bands_balanced",
+    "BatchLloyd", "shard_meshes",
 ]

@@ -40,10 +40,12 @@ static int fail(int code, const char *fmt, ...) {
     } while (0)
 
 long long g_srm_launches = 0;
+static thread_local bool g_pdl_suppress = false;   // set while a CUDA graph is being captured (plain edges there)
 bool srm_pdl_enabled() {
 #ifdef SRM_NO_PDL
     return false;
 #endif
+    if (g_pdl_suppress) return false;
     static const bool on = []() { const char *e = getenv("SRM_PDL"); return !(e && e[0] == '0'); }();
     return on;
 }
@@ -116,10 +118,17 @@ struct srm_ctx {
     SrmHash hash[2];           // pixel -> site id (and the dedupe claims of the update)
     int dbg_stats = 0;
     bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
+    // option "graph": srm_iterate replays a captured CUDA graph of 10 iterations (the period of the loop: buffer
+    // parity 2, energy every 10th) instead of launching 50 kernels from the host — for launch-bound sizes / batches
+    bool use_graph = false;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};   // [stop_rule]
+    int graph_key = 0;         // configuration the graphs were captured for (invalidated when it changes)
+    int graph_kernels[2] = {0, 0};   // kernel nodes per graph (for srm_launch_count)
     SrmCtl *ctl = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int it_host = 0;   // iterations executed since the sites were set (host mirror of SrmCtl::it)
     bool stopped = false;
+    bool unsynced = false;   // srm_iterate with the stop rule returned without reading the device's iteration count back
     void *comm = nullptr;  // NCCL communicator of the row bands (world > 1)
     int world = 1;
     // fused all-reduce over peer memory
@@ -131,6 +140,10 @@ struct srm_ctx {
     int **d_peer_flags = nullptr;
     std::vector<void *> ipc_opened;
 };
+
+static void drop_graphs(srm_ctx *c) {
+    for (int i = 0; i < 2; ++i) if (c->graph[i]) { cudaGraphExecDestroy(c->graph[i]); c->graph[i] = nullptr; }
+}
 
 static int valid_n(int n) { return n >= 256 && n <= 32768 && (n % 256) == 0; }
 
@@ -145,6 +158,7 @@ static int alloc_sites(srm_ctx *c, int K) {
     if (c->world > 1)   // peer mappings (srm_p2p_connect) and the NCCL element count refer to the current buffers
         return fail(SRM_ERR_STATE, "site set of %d entries exceeds the capacity %d the row-band collective was set up "
                                    "with: destroy the band contexts and reconnect", K, c->Kcap);
+    drop_graphs(c);   // captured kernel arguments point into the buffers freed below
     for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
     for (int i = 0; i < 2; ++i) if (c->hash[i].b) { cudaFree(c->hash[i].b); c->hash[i].b = nullptr; }
     if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
@@ -183,6 +197,7 @@ static int reset_ctl(srm_ctx *c, int K) {
     CK(cudaStreamSynchronize(c->stream));  // h is a stack object
     c->it_host = 0;
     c->stopped = false;
+    c->unsynced = false;
     c->labelled = false;
     return SRM_OK;
 }
@@ -276,6 +291,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (!c) return SRM_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    drop_graphs(c);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->flags) cudaFree(c->flags);
@@ -595,10 +611,20 @@ static int fetch_ctl(srm_ctx *c, SrmCtl *h) {
     CK(cudaStreamSynchronize(c->stream));
     c->it_host = h->it;  // iterations enqueued after a device-side stop were no-ops
     c->stopped = h->stop != 0;
+    c->unsynced = false;
     if (h->p2p_timeout)
         return fail(SRM_ERR_CUDA, "row-band all-reduce: a peer never signalled iteration %d (rank %d of %d gave up waiting); "
                                   "the site lists are no longer consistent", h->it + 1, c->rank, c->world);
     return SRM_OK;
+}
+
+// srm_iterate with the stopping rule does not wait for the device (batches of contexts are enqueued back to back): the
+// host mirror of the iteration count — the buffer parity of everything that follows — is read back by the next call
+// that needs it.
+static int resync(srm_ctx *c) {
+    if (!c->unsynced) return SRM_OK;
+    SrmCtl h;
+    return fetch_ctl(c, &h);
 }
 
 // The live site list is in sites[it & 1]: every executed iteration flips the buffer.
@@ -669,6 +695,7 @@ extern "C" int srm_debug_get(srm_ctx *c, int which, long long *value) {
 extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
     if (!c || !name) return fail(SRM_ERR_ARG, "srm_set_option: null argument");
     if (!strcmp(name, "robust_only")) { c->robust_only = value != 0; return SRM_OK; }
+    if (!strcmp(name, "graph")) { c->use_graph = value != 0; return SRM_OK; }
     if (!strcmp(name, "dbg_stats")) {
         c->dbg_stats = value;
         CK(cudaStreamSynchronize(c->stream));
@@ -789,6 +816,8 @@ static int ensure_rle(srm_ctx *c) {
 extern "C" int srm_label(srm_ctx *c) {
     int rc = require_ready(c, "srm_label", false);
     if (rc) return rc;
+    rc = resync(c);
+    if (rc) return rc;
     CK(cudaSetDevice(c->device));
     rc = label_with(c, c->it_host, 0, 0, 0);
     if (rc) return rc;
@@ -803,6 +832,8 @@ extern "C" int srm_label(srm_ctx *c) {
 extern "C" int srm_label_accumulate(srm_ctx *c, int want_energy) {
     int rc = require_ready(c, "srm_label_accumulate", true);
     if (rc) return rc;
+    rc = resync(c);
+    if (rc) return rc;
     CK(cudaSetDevice(c->device));
     rc = label_with(c, c->it_host, 0, 1, want_energy);
     if (rc) return rc;
@@ -814,6 +845,8 @@ extern "C" int srm_label_accumulate(srm_ctx *c, int want_energy) {
 
 extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     int rc = require_ready(c, "srm_accumulate", true);
+    if (rc) return rc;
+    rc = resync(c);
     if (rc) return rc;
     if (!c->labelled) return fail(SRM_ERR_STATE, "srm_accumulate: call srm_label first");
     CK(cudaSetDevice(c->device));
@@ -827,6 +860,7 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
 extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles) {
     if (!c || !device_ptr || !num_doubles) return fail(SRM_ERR_ARG, "srm_acc_buffer: null argument");
     if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_acc_buffer: sites not set");
+    { int rc = resync(c); if (rc) return rc; }
     *device_ptr = cur_acc(c, c->it_host);
     *num_doubles = 4 * (size_t)c->Kcap + 4;
     return SRM_OK;
@@ -837,6 +871,8 @@ extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles
 // caller reads srm_get_state when it wants to stop), omega still follows gcvt.cu:1131.
 extern "C" int srm_update(srm_ctx *c) {
     int rc = require_ready(c, "srm_update", true);
+    if (rc) return rc;
+    rc = resync(c);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
     // (stepwise mode with world > 1 and no bound collective is the caller-side all-reduce of ShardedLloyd.step:
@@ -851,32 +887,75 @@ extern "C" int srm_update(srm_ctx *c) {
     return SRM_OK;
 }
 
+// One Lloyd iteration on the context's stream (the body of the loop at gcvt.cu:1112-1123).
+static int one_iteration(srm_ctx *c, int it, int stop_rule) {
+    const int buf = it & 1, want_energy = (it % 10) == 0;
+    int rc = label_with(c, it, 1, 1, want_energy, /*write_rle=*/0);
+    if (rc) return rc;
+    rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
+    if (rc) return rc;
+    srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->nzbits,
+                      c->has_mask ? c->maskbits : nullptr, c->g, c->ctl, c->Kcap, c->newpos, step_of(c, it), want_energy,
+                      stop_rule, 1, peers_of(c, it));
+    return SRM_OK;
+}
+
+// Graph of iterations 10 q .. 10 q + 9: the kernel arguments depend on the iteration only through its parity and
+// through "every 10th computes the energy", and the stop flag / iteration counter live on the device, so one graph
+// serves every block of ten.  Captured without the PDL attribute (plain kernel-to-kernel edges).
+static int capture_graph(srm_ctx *c, int stop_rule) {
+    const int key = (c->Kcap << 3) ^ (c->has_mask ? 1 : 0) ^ (c->robust_only ? 2 : 0) ^ (c->dbg_stats ? 4 : 0) ^ (c->p2p ? 0x40000000 : 0);
+    if (key != c->graph_key) { drop_graphs(c); c->graph_key = key; }
+    if (c->graph[stop_rule]) return SRM_OK;
+    cudaGraph_t g = nullptr;
+    g_pdl_suppress = true;
+    const long long count0 = srm_launch_count();
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    int rc = SRM_OK;
+    if (e == cudaSuccess) {
+        for (int it = 0; it < 10 && rc == SRM_OK; ++it) rc = one_iteration(c, it, stop_rule);
+        e = cudaStreamEndCapture(c->stream, &g);
+    }
+    g_pdl_suppress = false;
+    c->graph_kernels[stop_rule] = (int)(srm_launch_count() - count0);
+    SRM_COUNT_N(-c->graph_kernels[stop_rule]);   // captured, not launched
+    if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(SRM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e)); }
+    e = cudaGraphInstantiate(&c->graph[stop_rule], g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) { c->graph[stop_rule] = nullptr; return fail(SRM_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e)); }
+    return SRM_OK;
+}
+
 extern "C" int srm_iterate(srm_ctx *c, int iters, int stop_rule) {
     int rc = require_ready(c, "srm_iterate", true);
     if (rc) return rc;
     rc = require_collective(c, "srm_iterate");
     if (rc) return rc;
+    rc = resync(c);
+    if (rc) return rc;
     CK(cudaSetDevice(c->device));
     if (c->stopped) return SRM_OK;
     int it = c->it_host;
-    for (int i = 0; i < iters; ++i, ++it) {
-        const int buf = it & 1, want_energy = (it % 10) == 0;
-        rc = label_with(c, it, 1, 1, want_energy, /*write_rle=*/0);
+    const int end = it + iters;
+    const bool graphs = c->use_graph && !c->comm;   // (an NCCL all-reduce inside the loop is not captured)
+    while (it < end) {
+        if (graphs && it % 10 == 0 && end - it >= 10) {
+            rc = capture_graph(c, stop_rule ? 1 : 0);
+            if (rc) return rc;
+            CK(cudaGraphLaunch(c->graph[stop_rule ? 1 : 0], c->stream));
+            SRM_COUNT_N(c->graph_kernels[stop_rule ? 1 : 0]);
+            it += 10;
+            continue;
+        }
+        rc = one_iteration(c, it, stop_rule);
         if (rc) return rc;
-        rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
-        if (rc) return rc;
-        srm_launch_update(c->stream, c->sites[buf], c->sites[buf ^ 1], c->acc, c->nzbits,
-                          c->has_mask ? c->maskbits : nullptr, c->g, c->ctl, c->Kcap, c->newpos, step_of(c, it), want_energy,
-                          stop_rule, 1, peers_of(c, it));
+        ++it;
     }
     CK(cudaGetLastError());
     c->it_host = it;
     c->labelled = false;
-    if (stop_rule) {  // the device may have stopped early: resynchronise the host mirror
-        SrmCtl h;
-        rc = fetch_ctl(c, &h);
-        if (rc) return rc;
-    }
+    c->unsynced = stop_rule != 0;   // the device may stop early: the next call that needs the count reads it back
     return SRM_OK;
 }
 
@@ -888,6 +967,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
     if (rc) return rc;
     if (!stage_ms || iters <= 0) return fail(SRM_ERR_ARG, "srm_iterate_profiled: bad argument");
     rc = require_collective(c, "srm_iterate_profiled");
+    if (rc) return rc;
+    rc = resync(c);
     if (rc) return rc;
     CK(cudaSetDevice(c->device));
     for (int k = 0; k < 6; ++k) stage_ms[k] = 0;
@@ -999,6 +1080,8 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
 
 extern "C" int srm_label_jfa(srm_ctx *c, const int *steps, int nsteps, short *out, int on_device) {
     int rc = require_ready(c, "srm_label_jfa", false);
+    if (rc) return rc;
+    rc = resync(c);
     if (rc) return rc;
     if (!steps || nsteps <= 0 || !out) return fail(SRM_ERR_ARG, "srm_label_jfa: bad argument");
     if (c->g.row0 != 0 || c->g.row1 != c->g.n) return fail(SRM_ERR_ARG, "srm_label_jfa: whole-grid contexts only");

@@ -448,10 +448,9 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             if (pos >= mb) break;
             if (m + 62 > C) { overflow = true; break; }  // the envelope itself does not fit
         }
-        // the accumulation ring needs one stage of free space behind the runs
+        // the accumulation ring lives in the free space behind the runs (rows too close to the capacity: plain loads)
         const int m4 = (m + 3) & ~3;
         const int stage_bytes = BAND_STAGE_BYTES(want_energy);
-        if (accumulate && (C - m4) * 4 < stage_bytes) overflow = true;
         if (overflow) {
             if (lane == 0) ovf_rows[atomicAdd(&ctl->ovf, 1)] = r;
             continue;
@@ -503,24 +502,61 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
             // sites in the pixel -> id hash are fetched by cp.async into a ring of 32-run stages behind the runs in this
             // warp's buffer.
             unsigned char *ring = reinterpret_cast<unsigned char *>(buf + m4);
-            const int nst = min(BAND_NST, ((C - m4) * 4) / stage_bytes);   // >= 1 (checked above)
+            const int nst = min(BAND_NST, ((C - m4) * 4) / stage_bytes);   // 0: no room for a stage
             const int nbat = (m + 31) >> 5;
             const double2 *p2 = P2 + srm_pfx_row(r, n);   // tiled layout: element x at [x * SRM_PFX_TILE]
             const double *pxx = PXX + srm_pfx_row(r, n);
             unsigned char *touched = reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4);
+            // run e with prefix entries pb (at its end) and pa (at the end of the previous run) -> its site's sums
+            auto apply = [&](unsigned v, int id, double2 pb, double2 pa, double xb, double xa) {
+                const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+                const double W = pb.x - pa.x, X = pb.y - pa.y;
+                double *a = acc + 4 * (size_t)id;
+                if (!ABL(2)) {
+                    atomicAdd(a, W);
+                    atomicAdd(a + 1, X);
+                    atomicAdd(a + 2, (double)Y * W);
+                    if (flags & SRM_BF_TOUCH) touched[id] = 1;
+                }
+#ifdef SRM_MEASURE
+                else if (W == -1.5) a[3] = X;   // keeps the loads alive when the atomics are ablated
+#endif
+                if (want_energy) e_loc += (xb - xa) - 2.0 * (double)x * X + (double)(x * x + g * g) * W;
+            };
+            auto run_end = [&](int e, unsigned v) {   // last pixel of run e (exact integer breakpoint with its successor)
+                if (e + 1 >= m) return n - 1;
+                const unsigned vn = buf[e + 1] & 0x7fffffffu;
+                const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
+                const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y;
+                return breakpoint(xn * xn + gn * gn - (x * x + g * g), 2 * (xn - x), n);
+            };
+            double2 carryP = make_double2(0, 0);
+            double carryXX = 0;
+            if (nst == 0) {
+                // a row whose runs leave no room for a stage: plain loads, neighbour by shuffle (the round-1 form)
+                for (int b = 0; b < nbat; ++b) {
+                    const int e = 32 * b + lane;
+                    const bool valid = e < m;
+                    const unsigned v = valid ? (buf[e] & 0x7fffffffu) : 0u;
+                    const int B = valid ? run_end(e, v) : 0;
+                    const double2 pb = valid ? p2[(size_t)B * SRM_PFX_TILE] : make_double2(0, 0);
+                    const double xb = (valid && want_energy) ? pxx[(size_t)B * SRM_PFX_TILE] : 0;
+                    const int id = valid ? max(srm_hash_find(hash, v), 0) : 0;
+                    double2 pa;
+                    pa.x = __shfl_up_sync(0xffffffffu, pb.x, 1); pa.y = __shfl_up_sync(0xffffffffu, pb.y, 1);
+                    double xa = __shfl_up_sync(0xffffffffu, xb, 1);
+                    if (lane == 0) { pa = carryP; xa = carryXX; }
+                    carryP.x = __shfl_sync(0xffffffffu, pb.x, 31); carryP.y = __shfl_sync(0xffffffffu, pb.y, 31);
+                    carryXX = __shfl_sync(0xffffffffu, xb, 31);
+                    if (valid) apply(v, id, pb, pa, xb, xa);
+                }
+            } else {
             auto issue = [&](int b) {
                 unsigned char *st = ring + (b % nst) * stage_bytes;
                 const int e = 32 * b + lane;
                 if (e < m) {
                     const unsigned v = buf[e] & 0x7fffffffu;
-                    const int x = (int)(v & 0xffffu), c = (int)(v >> 16), g = c - Y;
-                    int B = n - 1;
-                    if (e + 1 < m) {
-                        const unsigned vn = buf[e + 1] & 0x7fffffffu;
-                        const int xn = (int)(vn & 0xffffu), gn = (int)(vn >> 16) - Y;
-                        B = breakpoint(xn * xn + gn * gn - (x * x + g * g), 2 * (xn - x), n);
-                    }
-                    (void)c;
+                    const int B = run_end(e, v);
                     if (!ABL(8)) cp_async16(st + 16 * lane, p2 + (size_t)B * SRM_PFX_TILE);
                     if (!ABL(4)) cp_async16(st + 512 + 16 * lane, hash.b + srm_hash_bucket(hash, v));
                     if (want_energy) cp_async8(st + 1024 + 8 * lane, pxx + (size_t)B * SRM_PFX_TILE);
@@ -528,8 +564,6 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                 cp_async_commit();   // one group per batch, empty ones included: uniform group accounting
             };
             for (int b = 0; b < nst; ++b) issue(b);
-            double2 carryP = make_double2(0, 0);
-            double carryXX = 0;
             for (int b = 0; b < nbat; ++b) {
                 cp_async_wait_pending(nst - 1);
                 __syncwarp();   // the stage holds every lane's entries
@@ -548,24 +582,13 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                     const int id = ABL(4) ? (e + 37 * r) % Kcap
                                           : max(srm_hash_find_from(hash, v, srm_hash_bucket(hash, v),
                                                                    reinterpret_cast<const uint4 *>(st + 512)[lane]), 0);
-                    const int x = (int)(v & 0xffffu), g = (int)(v >> 16) - Y;
-                    const double W = pb.x - pa.x, X = pb.y - pa.y;
-                    double *a = acc + 4 * (size_t)id;
-                    if (!ABL(2)) {
-                        atomicAdd(a, W);
-                        atomicAdd(a + 1, X);
-                        atomicAdd(a + 2, (double)Y * W);
-                        if (flags & SRM_BF_TOUCH) touched[id] = 1;
-                    }
-#ifdef SRM_MEASURE
-                    else if (W == -1.5) a[3] = X;   // keeps the loads alive when the atomics are ablated
-#endif
-                    if (want_energy) e_loc += (xb - xa) - 2.0 * (double)x * X + (double)(x * x + g * g) * W;
+                    apply(v, id, pb, pa, xb, xa);
                 }
                 __syncwarp();   // every lane has read the stage before it is refilled
                 if (b + nst < nbat) issue(b + nst); else cp_async_commit();
             }
             cp_async_wait<0>();
+            }
         }
         __syncwarp();
         PROF_ADD(5);   // output + accumulate

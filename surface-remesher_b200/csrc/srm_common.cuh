@@ -132,6 +132,7 @@ struct SrmPeers {
 // over its timed region as gpu_launches).  Every `<<<>>>` site counts itself: SRM_COUNT(), k_x<<<...>>>(...).
 extern long long g_srm_launches;
 #define SRM_COUNT() ((void)__sync_fetch_and_add(&g_srm_launches, 1ll))
+#define SRM_COUNT_N(k) ((void)__sync_fetch_and_add(&g_srm_launches, (long long)(k)))
 
 // ---- Programmatic dependent launch (PDL): the kernels of the Lloyd loop are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so that a kernel's CTAs are scheduled while its predecessor
