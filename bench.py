@@ -179,6 +179,13 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, k, K, W = args.n, args.sites, args.steps, args.warmup
+    if args.only_c4:   # measurement helper: just the configs[3] leg (e.g. to compare band partitions)
+        c4 = run_c4(args, world, rank, local, dist if world > 1 else None)
+        if rank == 0:
+            print(json.dumps({"c4": c4}), flush=True)
+        if world > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
     dens, mask, vor = make_inputs(n, k, pinned=False)   # pageable numpy buffers, like the reference's caller
     nmask = int(mask.sum())
     # row bands of equal work (sites per block of rows), from the replicated seed map: identical on every rank
@@ -529,6 +536,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--c4-steps", dest="c4_steps", type=int, default=30,
                     help="timed steps of the BASELINE configs[3] leg (32768^2, 10^6 sites) appended to the line as `c4`; 0 = skip")
+    ap.add_argument("--only-c4", dest="only_c4", action="store_true", help="run only the configs[3] leg")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl", "py"],
                     help="N>1: p2p = fused all-reduce over peer memory inside the update kernel (default); nccl = NCCL "
                          "all-reduce issued by libsrm; py = torch.distributed all-reduce per step from Python")

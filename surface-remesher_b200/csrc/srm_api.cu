@@ -776,9 +776,10 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
+    // (fused all-reduce: the last CTA of the row kernel signals the peers that this rank's sums are complete)
     CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), rows, count, c->P2, c->PXX, s.hash,
-                      acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, write_rle));
-    if (accumulate) srm_launch_signal(c->stream, c->ctl, peers_of(c, it), respect_stop);
+                      acc, c->Kcap, c->ctl, accumulate, want_energy, respect_stop, write_rle,
+                      accumulate ? peers_of(c, it) : SrmPeers()));
     return SRM_OK;
 }
 
@@ -993,9 +994,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         }
         CK(cudaEventRecord(e[2], c->stream));
         CK(srm_launch_row(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), rows, count, c->P2, c->PXX, s.hash,
-                          acc, c->Kcap, c->ctl, 1, want_energy, 1, 0));
+                          acc, c->Kcap, c->ctl, 1, want_energy, 1, 0, peers_of(c, it)));
         CK(cudaEventRecord(e[3], c->stream));
-        srm_launch_signal(c->stream, c->ctl, peers_of(c, it), 1);
         rc = allreduce_acc(c);
         if (rc) return rc;
         CK(cudaEventRecord(e[4], c->stream));

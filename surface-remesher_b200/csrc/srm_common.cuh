@@ -24,6 +24,7 @@ struct SrmCtl {
     int band_ticket; // next band of the persistent band kernel (reset with ovf by k_bits)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
+    int row_ticket;  // robust row kernel: CTAs done (the last one signals the peers in the fused all-reduce)
     int rle_used;    // entries of the run-length pool handed out by the current labelling (reset by the carry kernel)
     int rle_fail;    // a row found the pool exhausted (its offset is -1): the host grows the pool and labels again
     float escale;    // multires: energy factor 4^level (gcvt.cu:1082); 1 on the finest level
@@ -170,8 +171,9 @@ struct SrmRle {
     int scratch_ctas = 0;
 };
 __device__ __forceinline__ int srm_rle_alloc(const SrmRle &R, SrmCtl *ctl, int r, int count) {   // one thread per row
-    const int o = atomicAdd(&ctl->rle_used, count);
-    const bool ok = o + count <= R.cap;
+    const int padded = (count + 1) & ~1;   // rows start 16-byte aligned (bulk copies of a row's list, k_expand)
+    const int o = atomicAdd(&ctl->rle_used, padded);
+    const bool ok = o + padded <= R.cap;
     R.off[r] = ok ? o : -1;
     R.cnt[r] = count;
     if (!ok) atomicExch(&ctl->rle_fail, 1);
@@ -219,7 +221,7 @@ cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
                            const int *rows, const int *count, const double2 *P2, const double *PXX,
                            SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
-                           int respect_stop, int write_rle);
+                           int respect_stop, int write_rle, SrmPeers signal = SrmPeers());
 int srm_row_scratch_ctas(int nrows);   // CTAs of the robust row kernel (= n-entry slices of SrmRle::scratch)
 cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels);
 cudaError_t srm_label_setup(int n);  // opt-in shared memory sizes

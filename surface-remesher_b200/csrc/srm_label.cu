@@ -277,7 +277,8 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
                                                 const int *__restrict__ count, const double2 *__restrict__ P2,
                                                 const double *__restrict__ PXX, SrmHash hash,
                                                 double *__restrict__ acc, int Kcap, SrmCtl *ctl,
-                                                int accumulate, int want_energy, int respect_stop, int write_rle) {
+                                                int accumulate, int want_energy, int respect_stop, int write_rle,
+                                                SrmPeers peers) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned short sb_[ROW_NT], se_[ROW_NT];
     __shared__ int wtot[ROW_NW];
@@ -383,6 +384,24 @@ __global__ void __launch_bounds__(ROW_NT) k_row(const uint32_t *__restrict__ bit
         }
         __syncthreads();
     }
+    // Fused all-reduce over peer memory: this is the last kernel that adds to the accumulators of the iteration, so the
+    // last CTA to get here tells every peer "my sums of iteration it are complete" (what the one-warp k_signal launch
+    // did in round 1).  k_update_pos on the peers waits for these flags and then pulls the sums over NVLink.
+    if (peers.world > 1) {
+        __shared__ int last;
+        __syncthreads();
+        if (t == 0) {
+            __threadfence();
+            last = atomicAdd(&ctl->row_ticket, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (last && t < peers.world) {
+            if (t == 0) ctl->row_ticket = 0;
+            const int target = (ctl->epoch << 20) | (ctl->it + 1);
+            __threadfence_system();
+            *(volatile int *)(peers.flags[t] + peers.rank) = target;
+        }
+    }
 }
 
 static size_t row_smem_bytes(int n) { return (size_t)n * 6; }  // 192 KB at n = 32768
@@ -393,8 +412,6 @@ cudaError_t srm_label_setup(int n) {
     // per function, not per context: opt in for the largest grid (contexts of different sizes coexist)
     cudaError_t e = cudaFuncSetAttribute(k_row, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_smem_bytes(32768));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_expand, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 * (int)sizeof(int));
-    if (e != cudaSuccess) return e;
     return srm_band_setup(n);
 }
 
@@ -403,62 +420,86 @@ int srm_row_scratch_ctas(int nrows) { (void)nrows; return 148; }
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
                            const int *rows, const int *count, const double2 *P2, const double *PXX,
                            SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int accumulate, int want_energy,
-                           int respect_stop, int write_rle) {
+                           int respect_stop, int write_rle, SrmPeers signal) {
     // rows == nullptr: every row of the band (CTAs loop over the rows); else the listed rows
     const int grid = rows ? 148 : std::min(g.nrows(), rle.scratch_ctas);
     srm_launch_pdl(st, dim3(grid), dim3(ROW_NT), row_smem_bytes(g.n), k_row, bits, up, dn, g.n, g.row0, g.nrows(), rle, rows,
-                   count, P2, PXX, hash, acc, Kcap, ctl, accumulate, want_energy, respect_stop, write_rle);
+                   count, P2, PXX, hash, acc, Kcap, ctl, accumulate, want_energy, respect_stop, write_rle, signal);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ runs -> dense labels
 
 #define EXP_NT 256
-// One CTA per row: scatter the run heads into a shared row, then a "last valid value" scan.
+#define EXP_CAP 4096   // runs of a row staged in shared memory (32 KB); longer rows are searched in global memory
+
+// ---- TMA 1-D bulk copy global -> shared with an mbarrier (sm_90+: SASS UBLKCP + SYNCS)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src_gmem),
+                 "r"(bytes), "r"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+
+// Runs -> dense labels, one CTA per row.  The row's run list ({site, first X}, sorted by X; rows allocate an even number
+// of entries, so it is 16-byte aligned) is fetched with ONE bulk copy (TMA) into shared memory; every thread then fills
+// groups of 4 pixels: binary search of the group's first pixel among the run starts (neighbouring threads probe the
+// same entries: broadcasts), at most three advances inside the group, one 128-bit store.  4 B/px written, nothing else
+// per pixel — the round-1 kernel built the row in shared memory (fill, scatter, scan: three passes over 4 B/px of
+// shared memory and a block-wide scan) and reached 41 % of the HBM write rate.
 __global__ void __launch_bounds__(EXP_NT) k_expand(SrmRle R, int n, int *__restrict__ labels) {
-    extern __shared__ __align__(16) int buf[];
-    __shared__ int wlast[EXP_NT / 32];
-    const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    extern __shared__ __align__(16) int2 s_runs[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int r = blockIdx.x, t = threadIdx.x;
     if (R.off[r] < 0) return;   // the pool was exhausted: the host repeats the labelling with a larger one
     const int cnt = R.cnt[r];
-    const int2 *rr = R.pool + R.off[r];
-    for (int i = t; i < n; i += EXP_NT) buf[i] = SRM_SENT;
-    __syncthreads();
-    for (int e = t; e < cnt; e += EXP_NT) { int2 v = rr[e]; buf[v.y] = v.x; }
-    __syncthreads();
-    int carry = SRM_SENT;
+    const int2 *runs = R.pool + R.off[r];
+    if (cnt == 0) {   // no site at all
+        for (int i = t; i < n; i += EXP_NT) labels[(size_t)r * n + i] = SRM_SENT;
+        return;
+    }
+    if (cnt <= EXP_CAP) {
+        if (t == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (t == 0) bulk_load(s_runs, runs, (unsigned)(((cnt + 1) & ~1) * sizeof(int2)), &bar);
+        mbar_wait(&bar, 0);
+        runs = s_runs;
+    }
     int4 *out = reinterpret_cast<int4 *>(labels + (size_t)r * n);
-    for (int base = 0; base < n; base += 4 * EXP_NT) {
-        const int q = (base >> 2) + t;
-        const bool in = (q << 2) < n;
-        int4 v = in ? reinterpret_cast<int4 *>(buf)[q] : make_int4(SRM_SENT, SRM_SENT, SRM_SENT, SRM_SENT);
-        int last = v.w != SRM_SENT ? v.w : v.z != SRM_SENT ? v.z : v.y != SRM_SENT ? v.y : v.x;
-        int x = last;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o && x == SRM_SENT) x = y;
+    for (int q = t; q < (n >> 2); q += EXP_NT) {
+        const int x = q << 2;
+        int lo = 0, hi = cnt;   // largest e with start(e) <= x; start(0) == 0
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (runs[mid].y <= x) lo = mid; else hi = mid;
         }
-        int excl = __shfl_up_sync(0xffffffffu, x, 1);
-        if (lane == 0) excl = SRM_SENT;
-        if (lane == 31) wlast[w] = x;
-        __syncthreads();
-        int cw = carry;
-        for (int k = 0; k < w; ++k) if (wlast[k] != SRM_SENT) cw = wlast[k];
-        int inval = excl != SRM_SENT ? excl : cw;
-        if (v.x == SRM_SENT) v.x = inval;
-        if (v.y == SRM_SENT) v.y = v.x;
-        if (v.z == SRM_SENT) v.z = v.y;
-        if (v.w == SRM_SENT) v.w = v.z;
-        if (in) out[q] = v;
-        for (int k = 0; k < EXP_NT / 32; ++k) if (wlast[k] != SRM_SENT) carry = wlast[k];
-        __syncthreads();
+        int e = lo;
+        int4 v;
+        v.x = runs[e].x;
+        if (e + 1 < cnt && runs[e + 1].y <= x + 1) ++e;
+        v.y = runs[e].x;
+        if (e + 1 < cnt && runs[e + 1].y <= x + 2) ++e;
+        v.z = runs[e].x;
+        if (e + 1 < cnt && runs[e + 1].y <= x + 3) ++e;
+        v.w = runs[e].x;
+        out[q] = v;
     }
 }
 
 cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels) {
-    size_t sm = (size_t)g.n * sizeof(int);
-    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, sm, st>>>(rle, g.n, labels);
+    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, EXP_CAP * sizeof(int2), st>>>(rle, g.n, labels);
     return cudaGetLastError();
 }
 

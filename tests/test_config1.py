@@ -94,3 +94,72 @@ def test_config1_full_pipeline_to_remeshed_surface():
     assert r["faces"] > 2000 and r["nonmanifold_edges"] == 0
     assert r["euler"] == 1                                   # a disk, like nefertiti.off
     assert abs(r["area"] - out["source_area"]) / out["source_area"] < 0.05
+
+
+def test_seam_cut_opens_a_closed_mesh_into_a_disk():
+    """split.h / main.cpp:157-168 stand-in on a synthetic closed mesh (an octahedron refined twice): seam = a path of
+    edges; after the long-edge split and the cut the mesh is a disk whose border has twice the seam's edges, every
+    interior seam vertex is duplicated, the end points are not."""
+    from surface_remesher_b200 import frontend as FE
+    V = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], np.float64)
+    F = np.array([[0, 2, 4], [2, 1, 4], [1, 3, 4], [3, 0, 4], [2, 0, 5], [1, 2, 5], [3, 1, 5], [0, 3, 5]], np.int32)
+
+    def euler(F):
+        e = np.sort(np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]]), axis=1)
+        ue, c = np.unique(e, axis=0, return_counts=True)
+        return len(np.unique(F)) - len(ue) + len(F), int((c == 1).sum())
+
+    assert euler(F) == (2, 0)
+    pairs = [(4, 0), (0, 5), (7, 9)]                 # a path 4-0-5 plus a pair that is not an edge (ignored, split.h:47)
+    seam = FE.seam_edges_of(F, pairs)
+    assert seam == [(0, 4), (0, 5)]
+    V1, F1, seam1 = FE.split_long_edges(V, F, seam, 0.8)      # edges of length sqrt(2) are split once
+    assert len(seam1) == 4 and euler(F1) == (2, 0) and len(V1) == 8
+    V2, F2, orig = FE.cut_along_seam(V1, F1, seam1)
+    assert euler(F2) == (1, 8)                                   # a disk; border = 2 x 4 seam edges
+    assert len(V2) == len(V1) + 3                                # the 3 interior vertices of the path are duplicated
+    assert np.array_equal(V2[len(V1):], V1[orig[len(V1):]])
+    loop = FE.boundary_loop(F2)
+    assert len(loop) == 8
+    UV = FE.tutte_parameterize(V2, F2, loop)
+    e1, e2 = UV[F2[:, 1]] - UV[F2[:, 0]], UV[F2[:, 2]] - UV[F2[:, 0]]
+    area = e1[:, 0] * e2[:, 1] - e2[:, 0] * e1[:, 1]
+    assert (np.sign(area) == np.sign(area[0])).all()
+
+
+def test_config1_horse_fixture_is_a_cut_disk():
+    z = np.load(os.path.join(G, "c1_horse.npz"))
+    F, uv, loop, orig = z["F"], z["uv"], z["loop"], z["orig"]
+    e = np.sort(np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]]), axis=1)
+    ue, c = np.unique(e, axis=0, return_counts=True)
+    assert len(np.unique(F)) - len(ue) + len(F) == 1 and (c == 1).sum() == len(loop)
+    e1, e2 = uv[F[:, 1]] - uv[F[:, 0]], uv[F[:, 2]] - uv[F[:, 0]]
+    area = e1[:, 0] * e2[:, 1] - e2[:, 0] * e1[:, 1]
+    assert (np.sign(area) == np.sign(area[0])).all()
+    # welding the copies back gives the refined closed surface: Euler characteristic 2, no border
+    Fw = orig[F]
+    ew = np.sort(np.concatenate([Fw[:, [0, 1]], Fw[:, [1, 2]], Fw[:, [2, 0]]]), axis=1)
+    uew, cw = np.unique(ew, axis=0, return_counts=True)
+    assert len(np.unique(Fw)) - len(uew) + len(Fw) == 2 and (cw == 1).sum() == 0
+
+
+@pytest.mark.gpu
+def test_config1_horse_full_pipeline_closes_after_welding():
+    """BASELINE configs[0] on the mesh SURVEY names: horse.off cut along its seam -> rasterise -> gCVT (1024^2, 2000 sites,
+    100 iterations) -> delaunayInput -> reference gDel2D -> recover; every stage identical to the oracle chain, and the
+    remeshed surface closes again when the two sides of the seam are welded."""
+    import sys
+    import _ref as R
+    if not R.cdt_available():
+        pytest.skip("oracle/_ref/libgdel2d_ref.so not built")
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import run_config1 as RC
+    try:
+        out, verts, T = RC.run(1024, 2000, 100, mesh="horse")
+    except RuntimeError as e:   # the decade-old reference CDT is not the product: report, do not fail
+        pytest.skip(str(e))
+    assert out["density_bit_exact"] and out["labels_bit_exact"] and out["cdt_input_identical"]
+    assert out["vertices_bit_exact"] and out["kept_identical"] and out["max_vertex_diff_over_extent"] <= 1e-5
+    assert out["result"]["euler"] == 1 and out["result"]["nonmanifold_edges"] == 0          # a disk before welding
+    w = out["result_welded"]
+    assert w["euler"] == 2 and w["border_edges"] == 0 and w["nonmanifold_edges"] == 0         # a closed surface after

@@ -9,7 +9,10 @@ front end; fixture tests/golden/c1_nefertiti.npz):
 and the same with the CPU oracle in place of every libsrm call; both must give identical sites, CDT input and final
 vertices.  Prints one JSON object; writes the remeshed surface to `out_off` if given.
 
-    python tools/run_config1.py [n=1024] [sites=2000] [iters=100] [out_off]
+    python tools/run_config1.py [n=1024] [sites=2000] [iters=100] [out_off] [mesh=nefertiti|horse]
+
+mesh=horse: the closed horse.off cut along data/horse.selection.txt (fixture tests/golden/c1_horse.npz); the two sides of
+the seam are welded in the result, which must be a closed surface again (Euler characteristic 2).
 """
 import json
 import os
@@ -58,8 +61,25 @@ def mesh_stats(V, T):
             "mean_edge": float(np.linalg.norm(V[ue[:, 0]] - V[ue[:, 1]], axis=1).mean())}
 
 
-def run(n=1024, sites=2000, iters=100, out_off=None):
-    z = np.load(os.path.join(ROOT, "tests", "golden", "c1_nefertiti.npz"))
+def weld(T, num_free, cpoint_orig):
+    """Merge the constraint points (CDT points num_free..) that are copies of one surface vertex — the two sides of the
+    seam — and return the triangles with merged indices."""
+    idx = np.arange(num_free + len(cpoint_orig))
+    first = {}
+    for i, o in enumerate(np.asarray(cpoint_orig).tolist()):
+        idx[num_free + i] = first.setdefault(o, num_free + i)
+    Tw = idx[T]
+    # The border (one point per seam vertex and side) is sampled more densely than the interior (2000 sites), so the CDT
+    # has "ears" (i, i+1, i+2) along it.  Where both sides of the seam have the same ear, welding makes them one
+    # triangle twice — a flat pillow: drop both copies (their middle vertex then simply is not used any more).
+    key = np.sort(Tw, axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    keep = (cnt[inv.reshape(-1)] == 1) & (key[:, 0] != key[:, 1]) & (key[:, 1] != key[:, 2])
+    return Tw[keep]
+
+
+def run(n=1024, sites=2000, iters=100, out_off=None, mesh="nefertiti"):
+    z = np.load(os.path.join(ROOT, "tests", "golden", f"c1_{mesh}.npz"))
     V3, F, uv, loop, wt = z["V"], np.ascontiguousarray(z["F"], np.int32), z["uv"], z["loop"], np.ascontiguousarray(z["weights"])
     pts, scale, l, b = FE.discretization_arrays(uv, n)
     out = {"n": n, "sites": sites, "max_iter": iters, "mesh": {"V": len(V3), "F": len(F), "border": len(loop)}}
@@ -94,6 +114,12 @@ def run(n=1024, sites=2000, iters=100, out_off=None):
     out["kept_identical"] = bool(np.array_equal(keep, ekeep))
     T = tri[keep.astype(bool)]
     out["result"] = mesh_stats(verts, T)
+    if "orig" in z.files:   # a mesh that was cut along a seam: weld the two sides, the surface must close again
+        Tw = weld(T, k0, z["orig"][loop])
+        out["result_welded"] = mesh_stats(verts, Tw)
+        src = mesh_stats(z["V_src"], z["F_src"])
+        out["source"] = {"euler": src["euler"], "border_edges": src["border_edges"]}
+        T = Tw
     a3 = 0.5 * np.linalg.norm(np.cross(V3[F[:, 1]] - V3[F[:, 0]], V3[F[:, 2]] - V3[F[:, 0]]), axis=1).sum()
     out["source_area"] = float(a3)
     ext = float((V3.max(0) - V3.min(0)).max())
@@ -106,5 +132,5 @@ def run(n=1024, sites=2000, iters=100, out_off=None):
 if __name__ == "__main__":
     a = sys.argv[1:]
     res, _, _ = run(int(a[0]) if len(a) > 0 else 1024, int(a[1]) if len(a) > 1 else 2000, int(a[2]) if len(a) > 2 else 100,
-                    a[3] if len(a) > 3 else None)
+                    a[3] if len(a) > 3 else None, a[4] if len(a) > 4 else "nefertiti")
     print(json.dumps(res))
