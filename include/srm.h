@@ -109,6 +109,13 @@ int srm_synchronize(srm_ctx *ctx);
 /* Inputs: full-grid arrays (n*n).  on_device != 0 means the pointer is device memory on ctx's device. */
 int srm_set_density(srm_ctx *ctx, const float *density, int on_device);
 int srm_set_mask(srm_ctx *ctx, const unsigned char *mask, int on_device); /* NULL = no constraints */
+/* Host scans of the two sparse inputs (multi-threaded; no device work), for callers that shard them: the sites of
+ * `pixels` seed-map pixels in row-major order (packed x | y << 16), and the non-zero pixels of rows [row0, row1) of a
+ * 1 B/px mask.  *count = number found (may exceed capacity; at most capacity entries are written). */
+int srm_scan_site_map_host(const short *site_map, size_t pixels, int *packed_out, int capacity, int *count);
+int srm_scan_mask_host(const unsigned char *mask, int n, int row0, int row1, int *packed_out, int capacity, int *count);
+/* The constraint pixels as a list (packed x | y << 16) instead of a 1 B/px mask. */
+int srm_set_mask_pixels(srm_ctx *ctx, const int *packed_xy, int count);
 /* Row bands without replicating the inputs: only the band's own rows of the density ((row1-row0)*n floats) ... */
 int srm_set_density_band(srm_ctx *ctx, const float *band_rows, int on_device);
 /* ... and the two full-grid bitmaps the replicated site update reads (which = 0: density != 0, 1: constraint pixels;

@@ -64,6 +64,9 @@ def lib():
     L.srm_set_density.argtypes = [p, p, i]
     L.srm_set_mask.argtypes = [p, p, i]
     L.srm_set_density_band.argtypes = [p, p, i]
+    L.srm_set_mask_pixels.argtypes = [p, p, i]
+    L.srm_scan_site_map_host.argtypes = [p, C.c_size_t, p, i, C.POINTER(i)]
+    L.srm_scan_mask_host.argtypes = [p, i, i, i, p, i, C.POINTER(i)]
     L.srm_shared_bits.argtypes = [p, i, C.POINTER(p), C.POINTER(C.c_size_t)]
     L.srm_set_site_map.argtypes = [p, p, i]
     L.srm_set_sites.argtypes = [p, p, i, i]
@@ -85,7 +88,7 @@ def lib():
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
-                 "srm_set_density_band", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
+                 "srm_set_density_band", "srm_set_mask_pixels", "srm_scan_site_map_host", "srm_scan_mask_host", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa"):
         getattr(L, name).restype = i
@@ -194,6 +197,35 @@ def recover(points_2d, points_3d, faces, points_xy, cpoint_vertex, cdt_triangles
                           cdt.ctypes.data_as(C.c_void_p) if len(cdt) else None, len(cdt), _np(out, np.float64),
                           _np(keep, np.uint8), C.byref(kept)))
     return out, keep[: len(cdt)]
+
+
+def scan_site_map(site_map_rows):
+    """Sites of (rows of) a dense seed map as a packed int32 list in row-major order (multi-threaded host scan)."""
+    a = np.ascontiguousarray(site_map_rows, np.int16)
+    pixels = a.size // 2
+    cnt = C.c_int()
+    cap = max(1024, pixels // 64)
+    while True:
+        out = np.empty(cap, np.int32)
+        _ck(lib().srm_scan_site_map_host(a.ctypes.data_as(C.c_void_p), pixels, out.ctypes.data_as(C.c_void_p), cap, C.byref(cnt)))
+        if cnt.value <= cap:
+            return out[: cnt.value]
+        cap = cnt.value
+
+
+def scan_mask(mask, n, row0, row1):
+    """Non-zero pixels of rows [row0, row1) of a 1 B/px mask as packed int32 (x | y << 16)."""
+    m = mask if (isinstance(mask, np.ndarray) and mask.dtype in (np.uint8, np.bool_) and mask.flags["C_CONTIGUOUS"]) \
+        else np.ascontiguousarray(mask, dtype=np.uint8)
+    cnt = C.c_int()
+    cap = 1 << 16
+    while True:
+        out = np.empty(cap, np.int32)
+        _ck(lib().srm_scan_mask_host(m.ctypes.data_as(C.c_void_p), int(n), int(row0), int(row1), out.ctypes.data_as(C.c_void_p), cap,
+                                     C.byref(cnt)))
+        if cnt.value <= cap:
+            return out[: cnt.value]
+        cap = cnt.value
 
 
 # ---------------------------------------------------------------- handle API
@@ -309,6 +341,11 @@ class Context:
         shared_bits(0) between the ranks."""
         p, dev = _ptr(band_rows)
         _ck(lib().srm_set_density_band(self._h, p, dev))
+
+    def set_mask_pixels(self, packed_xy):
+        """Constraint pixels as a packed list (x | y << 16, int32)."""
+        a = np.ascontiguousarray(packed_xy, np.int32)
+        _ck(lib().srm_set_mask_pixels(self._h, a.ctypes.data_as(C.c_void_p), int(a.shape[0])))
 
     def shared_bits(self, which):
         """(device pointer, number of 32-bit words) of a full-grid bitmap: 0 = density != 0, 1 = constraint pixels."""

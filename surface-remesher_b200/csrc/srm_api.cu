@@ -162,7 +162,7 @@ static int alloc_sites(srm_ctx *c, int K) {
     for (int i = 0; i < 2; ++i) if (c->sites[i]) { cudaFree(c->sites[i]); c->sites[i] = nullptr; }
     for (int i = 0; i < 2; ++i) if (c->hash[i].b) { cudaFree(c->hash[i].b); c->hash[i].b = nullptr; }
     if (c->acc) { cudaFree(c->acc); c->acc = nullptr; }
-    if (c->newpos) { cudaFree(c->newpos); c->newpos = nullptr; }
+    c->newpos = nullptr;   // lives behind the accumulator pair (one allocation, one IPC mapping for the peers)
     c->Kcap = K;
     size_t k1 = (size_t)(K > 0 ? K : 1);
     {   // hash tables: two-slot buckets, buckets = power of two >= 2 K (slot load <= 0.25, 16 bytes per bucket)
@@ -176,11 +176,11 @@ static int alloc_sites(srm_ctx *c, int K) {
     }
     CK(cudaMalloc(&c->sites[0], k1 * sizeof(int)));
     CK(cudaMalloc(&c->sites[1], k1 * sizeof(int)));
-    CK(cudaMalloc(&c->newpos, k1 * sizeof(int)));
     // two buffers (the peer-memory all-reduce alternates them by iteration parity), each: 4K+4 doubles of sums
     // followed by K "this rank contributed to the site" bytes
     c->acc_stride = (4 * (size_t)K + 4 + ((size_t)K + 7) / 8 + 3) & ~(size_t)3;  // 32-byte aligned buffers
-    CK(cudaMalloc(&c->acc, 2 * c->acc_stride * sizeof(double)));
+    CK(cudaMalloc(&c->acc, 2 * c->acc_stride * sizeof(double) + k1 * sizeof(int)));
+    c->newpos = reinterpret_cast<int *>(c->acc + 2 * c->acc_stride);   // peers store their slice of the new positions here
     CK(cudaMemsetAsync(c->acc, 0, 2 * c->acc_stride * sizeof(double), c->stream));
     c->p2p = false;  // peer mappings refer to the old buffers
     c->cur = 0;
@@ -274,13 +274,14 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->rle_off, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
-    CKD(cudaMalloc(&c->flags, 64 * sizeof(int)));
-    CKD(cudaMemsetAsync(c->flags, 0, 64 * sizeof(int), c->stream));
+    CKD(cudaMalloc(&c->flags, 128 * sizeof(int)));   // [0,64): sums complete, [64,128): newpos slice delivered, per rank
+    CKD(cudaMemsetAsync(c->flags, 0, 128 * sizeof(int), c->stream));
     c->blockcap = c->N / 256 + 2;  // covers both the seed-map compaction (N/1024 tiles) and K <= N sites
     CKD(cudaMalloc(&c->blockcnt, c->blockcap * sizeof(int)));
     CKD(cudaMalloc(&c->blockoff, c->blockcap * sizeof(int)));
     CKD(cudaMemsetAsync(c->ctl, 0, sizeof(SrmCtl), c->stream));
     CKD(srm_label_setup(n));
+    srm_preload_kernels();
     CKD(cudaStreamSynchronize(c->stream));
 #undef CKD
     *out = c;
@@ -297,7 +298,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->flags) cudaFree(c->flags);
     if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
     if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
-    void *ptrs[] = {c->density, c->nzbits, c->maskbits, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->newpos, c->blockcnt,
+    void *ptrs[] = {c->density, c->nzbits, c->maskbits, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->blockcnt,
                     c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->row_scratch, c->rle_cnt, c->rle_off, c->ovf_rows,
                     c->edge[0], c->edge[1], c->hash[0].b, c->hash[1].b, c->labels, c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -340,6 +341,10 @@ static SrmPeers peers_of(srm_ctx *c, int it) {
     if (c->p2p) {
         p.acc = c->d_peer_acc; p.flags = c->d_peer_flags; p.flags_local = c->flags;
         p.world = c->world; p.rank = c->rank; p.stride = c->acc_stride; p.parity = it & 1; p.kcap = c->Kcap;
+        // owner-computes pays one more kernel and flag exchange per iteration and saves (world-1)/world of the remote
+        // loads: measured break-even far above 10^5 sites (8192^2 / 100k: 33 -> 46 us per update on 2 GPUs; 32768^2 /
+        // 10^6: 420 -> 125 us)
+        p.owner = c->Kcap >= 300000;
     }
     return p;
 }
@@ -402,6 +407,7 @@ extern "C" int srm_p2p_connect(srm_ctx *c, const void *blobs, int rank, int worl
     CK(cudaMemcpy((void *)c->d_peer_acc, pa.data(), world * sizeof(void *), cudaMemcpyHostToDevice));
     CK(cudaMemcpy((void *)c->d_peer_flags, pf.data(), world * sizeof(void *), cudaMemcpyHostToDevice));
     c->world = world; c->rank = rank; c->p2p = world > 1;
+    srm_preload_kernels();
     return SRM_OK;
 }
 
@@ -512,6 +518,28 @@ extern "C" int srm_set_density_band(srm_ctx *c, const float *band_rows, int on_d
     return density_ready(c);
 }
 
+// The host scans of the sparse inputs (srm_host.cu), for callers that shard them: sites of `pixels` seed-map pixels
+// (packed x | y << 16 = the map's own values, row-major order) and the non-zero bytes of rows [row0, row1) of a mask.
+// Return the number found in *count (which may exceed `capacity`; only `capacity` entries are written).
+extern "C" int srm_scan_site_map_host(const short *site_map, size_t pixels, int *packed_out, int capacity, int *count) {
+    if (!site_map || !count || (!packed_out && capacity > 0)) return fail(SRM_ERR_ARG, "srm_scan_site_map_host: bad argument");
+    std::vector<int> v;
+    srm_scan_site_map((const int *)site_map, pixels, v);
+    *count = (int)v.size();
+    if (packed_out) memcpy(packed_out, v.data(), sizeof(int) * std::min((size_t)capacity, v.size()));
+    return SRM_OK;
+}
+
+extern "C" int srm_scan_mask_host(const unsigned char *mask, int n, int row0, int row1, int *packed_out, int capacity, int *count) {
+    if (!mask || !count || n <= 0 || (n % 8) || row0 < 0 || row1 > n || row0 > row1 || (!packed_out && capacity > 0))
+        return fail(SRM_ERR_ARG, "srm_scan_mask_host: bad argument");
+    std::vector<int> v;
+    srm_scan_mask(mask, n, v, row0, row1);
+    *count = (int)v.size();
+    if (packed_out) memcpy(packed_out, v.data(), sizeof(int) * std::min((size_t)capacity, v.size()));
+    return SRM_OK;
+}
+
 // Device pointers of the two full-grid bitmaps (which = 0: density != 0, 1: constraint pixels): n*n/32 words, row y
 // starts at word y*n/32.  For the exchange of the band slices between ranks.
 extern "C" int srm_shared_bits(srm_ctx *c, int which, void **device_ptr, size_t *num_words) {
@@ -535,6 +563,19 @@ static int set_mask_pixels(srm_ctx *c, const std::vector<int> &px) {
     }
     c->has_mask = true;
     return SRM_OK;
+}
+
+// Constraint pixels as a list (packed x | y << 16) instead of the 1 B/px mask: what srm_set_mask extracts from a host
+// mask.  Row bands: every rank scans its own rows of the mask and the lists are concatenated by the caller.
+extern "C" int srm_set_mask_pixels(srm_ctx *c, const int *packed_xy, int count) {
+    if (!c || (!packed_xy && count > 0) || count < 0) return fail(SRM_ERR_ARG, "srm_set_mask_pixels: bad argument");
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < count; ++i) {
+        const int x = srm_x(packed_xy[i]), y = srm_y(packed_xy[i]);
+        if (x < 0 || y < 0 || x >= c->g.n || y >= c->g.n) return fail(SRM_ERR_ARG, "srm_set_mask_pixels: pixel %d outside the grid", i);
+    }
+    std::vector<int> px(packed_xy, packed_xy + count);
+    return set_mask_pixels(c, px);
 }
 
 extern "C" int srm_set_mask(srm_ctx *c, const unsigned char *mask, int on_device) {

@@ -24,6 +24,7 @@ struct SrmCtl {
     int band_ticket; // next band of the persistent band kernel (reset with ovf by k_bits)
     int p2p_timeout; // set if a peer never arrived (fail-safe of the spin wait)
     int epoch;       // bumped whenever the sites are (re)set: arrival flags carry epoch << 20 | (it + 1), never reset
+    int pos_ticket;  // owner-computes update: blocks of k_update_pos done (the last one publishes the rank's newpos slice)
     int row_ticket;  // robust row kernel: CTAs done (the last one signals the peers in the fused all-reduce)
     int rle_used;    // entries of the run-length pool handed out by the current labelling (reset by the carry kernel)
     int rle_fail;    // a row found the pool exhausted (its offset is -1): the host grows the pool and labels again
@@ -122,11 +123,14 @@ __device__ __forceinline__ double warp_sum(double v) {
 struct SrmPeers {
     const double *const *acc = nullptr;  // device array [world]: base of every rank's accumulator pair
     int *const *flags = nullptr;         // device array [world]: every rank's arrival-flag array
-    int *flags_local = nullptr;          // this rank's flag array (slot q = last iteration rank q finished accumulating)
+    int *flags_local = nullptr;          // this rank's flag array: slot q = last iteration rank q finished accumulating,
+                                         // slot 64 + q = last iteration whose newpos slice rank q has delivered
     int world = 1, rank = 0;
     size_t stride = 0;                   // doubles per accumulator buffer (two buffers, used by iteration parity)
     int kcap = 0;                        // sites per buffer: 4*kcap+4 doubles of sums, then kcap "touched" bytes
     int parity = 0;
+    int owner = 0;                       // 1: owner-computes update (every rank updates 1/world of the ids and delivers the
+                                         // result to all peers); 0: every rank pulls the sums of all sites (small site sets)
 };
 
 // Kernel launches issued by this library since it was loaded (srm_launch_count(); bench.py reports the difference
@@ -238,6 +242,8 @@ void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, dou
 void srm_launch_nonzero_bits_f32(cudaStream_t st, const float *v, size_t count, uint32_t *out);
 void srm_launch_nonzero_bits_u8(cudaStream_t st, const unsigned char *v, size_t count, uint32_t *out);
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop);
+void srm_preload_kernels();   // resolves every kernel of the loop up front (lazy module loading may otherwise synchronise
+                              // the device in the middle of a launch sequence, while a kernel spins on a peer's flag)
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,
                                int *blockoff, int *total_out, int count_only);
 void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out);
@@ -267,7 +273,7 @@ cudaError_t srm_raster(cudaStream_t st, const double *pts, const double *wt, int
 cudaError_t srm_h2d_pageable(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t after);
 cudaError_t srm_d2h_pageable(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t after);
 void srm_scan_site_map(const int *site_map, size_t N, std::vector<int> &sites);
-void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels);
+void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels, int row0 = 0, int row1 = -1);
 void srm_host_pool_release();
 void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, uint32_t *maskbits);
 #endif

@@ -202,11 +202,12 @@ void srm_scan_site_map(const int *site_map, size_t N, std::vector<int> &sites) {
 }
 
 // Non-zero bytes of the constraint mask as packed pixels (x | y << 16), any order.
-void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels) {
+void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels, int row0, int row1) {
     const int T = pool_threads();
+    if (row1 < 0) row1 = n;
     std::vector<std::vector<int>> part((size_t)T);
     parallel(T, [&](int t) {
-        const int y0 = (int)((long long)n * t / T), y1 = (int)((long long)n * (t + 1) / T);
+        const int y0 = row0 + (int)((long long)(row1 - row0) * t / T), y1 = row0 + (int)((long long)(row1 - row0) * (t + 1) / T);
         std::vector<int> &out = part[(size_t)t];
         for (int y = y0; y < y1; ++y) {
             const unsigned long long *row = reinterpret_cast<const unsigned long long *>(mask + (size_t)y * n);

@@ -170,83 +170,134 @@ void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect
 // round 1: the update is replicated on every rank and may look at any pixel.
 __device__ __forceinline__ bool srm_bit(const uint32_t *__restrict__ b, size_t i) { return (b[i >> 5] >> (i & 31)) & 1u; }
 
+// Owner-computes form of the fused all-reduce (r2): with W ranks, rank r computes the new position only of the sites with
+// id in [K r / W, K (r+1) / W) — it pulls their partial sums from the ranks that contributed (remote loads over NVLink,
+// 1/W of what every rank pulled in round 1) — and stores the result into the newpos array of EVERY rank (remote stores,
+// coalesced).  The last block to finish tells every peer "my slice of newpos is complete"; k_update_claim waits for all
+// slices and then every rank runs the (cheap, replicated) claim + resolve on the complete list, so the site lists stay
+// identical without a broadcast of the list itself.
+__device__ __forceinline__ bool wait_flags(const int *flags, int world, int target, SrmCtl *ctl) {
+    for (int q = 0; q < world; ++q) {
+        long long spins = 0;
+        while (ld_volatile_int(flags + q) < target)
+            if (++spins > (1ll << 28)) {   // fail-safe: never hang the GPU.  Stop the loop (every later kernel returns
+                ctl->p2p_timeout = 1;      // at once) and let the host report it (fetch_ctl -> SRM_ERR_CUDA)
+                ctl->stop = 1;
+                return false;
+            }
+    }
+    return true;
+}
+
 __global__ void k_update_pos(const int *__restrict__ sites, const double *acc, const uint32_t *__restrict__ nzbits,
                              const uint32_t *__restrict__ maskbits, int n, SrmCtl *ctl, int *__restrict__ newpos,
                              SrmHash claim, int respect_stop, SrmPeers peers) {
+    __shared__ int s_last;
     srm_pdl_enter();
     if (respect_stop && ctl->stop) return;
-    if (peers.world > 1) {  // wait for every rank's accumulators of this iteration
-        if (threadIdx.x == 0) {
-            const int target = (ctl->epoch << 20) | (ctl->it + 1);
-            for (int q = 0; q < peers.world; ++q) {
-                long long spins = 0;
-                while (ld_volatile_int(peers.flags_local + q) < target)
-                    if (++spins > (1ll << 28)) {   // fail-safe: never hang the GPU.  The sums are incomplete: stop the
-                        ctl->p2p_timeout = 1;      // loop (every later kernel returns at once) and let the host
-                        ctl->stop = 1;             // report it (fetch_ctl -> SRM_ERR_CUDA)
-                        break;
-                    }
-            }
-        }
+    const bool pull = peers.world > 1;                  // the sums live in the peers' accumulators
+    const bool shared_update = pull && peers.owner;     // ... and this rank updates only its slice of the ids
+    if (pull) {  // wait for every rank's accumulators of this iteration
+        if (threadIdx.x == 0) wait_flags(peers.flags_local, peers.world, (ctl->epoch << 20) | (ctl->it + 1), ctl);
         __syncthreads();
         if (ctl->p2p_timeout) return;   // a peer never arrived: do not update from partial sums
     }
+    const int K = ctl->K;
+    // this rank's slice of the ids (everything on a single GPU / with the NCCL all-reduce)
+    const int lo = shared_update ? (int)((long long)K * peers.rank / peers.world) : 0;
+    const int hi = shared_update ? (int)((long long)K * (peers.rank + 1) / peers.world) : K;
+    const int id = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (id < hi) {
+        const int p = sites[id];
+        int np = SRM_SENT;
+        if (p != SRM_SENT) {
+            const int tx = srm_x(p), ty = srm_y(p);
+            int rx = tx, ry = ty;
+            if (!(maskbits && srm_bit(maskbits, (size_t)ty * n + tx))) {
+                double sW = 0, sX = 0, sY = 0;
+                if (pull) {
+                    // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
+                    // cell spans one or two bands, so only those ranks' sums are pulled over NVLink.  Remote loads cost
+                    // ~2 us each, so they are issued in independent batches of 8 ranks (all "touched" bytes, then all sums)
+                    // and added in rank order (bit-identical totals whoever computes them).
+                    for (int q0 = 0; q0 < peers.world; q0 += 8) {
+                        const double *base[8];
+                        unsigned char tch[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int q = min(q0 + k, peers.world - 1);
+                            base[k] = peers.acc[q] + (size_t)peers.parity * peers.stride;
+                            tch[k] = (q0 + k < peers.world)
+                                         ? __ldcv(reinterpret_cast<const unsigned char *>(base[k] + 4 * (size_t)peers.kcap + 4) + id)
+                                         : (unsigned char)0;
+                        }
+                        double2 wx[8];
+                        double yy[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            wx[k] = make_double2(0, 0); yy[k] = 0;
+                            if (tch[k]) {
+                                const double *a = base[k] + 4 * (size_t)id;
+                                wx[k] = __ldcv(reinterpret_cast<const double2 *>(a));
+                                yy[k] = __ldcv(a + 2);
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            if (tch[k]) { sW += wx[k].x; sX += wx[k].y; sY += yy[k]; }
+                    }
+                } else {
+                    const double *a = acc + 4 * (size_t)id;
+                    sW = a[0]; sX = a[1]; sY = a[2];
+                }
+                const float pW = (float)sW, pX = (float)sX, pY = (float)sY;
+                const float omega = ctl->omega;
+                const float _x = __fdiv_rn(pX, pW), _y = __fdiv_rn(pY, pW);
+                const float fx = __fadd_rn(__fmaf_rn(__fsub_rn(_x, (float)tx), omega, (float)tx), 0.5f);
+                const float fy = __fadd_rn(__fmaf_rn(__fsub_rn(_y, (float)ty), omega, (float)ty), 0.5f);
+                int cx = __float2int_rz(fx), cy = __float2int_rz(fy);  // NaN -> 0, like F2I.TRUNC
+                cx = max(min(cx, n - 1), 0);
+                cy = max(min(cy, n - 1), 0);
+                if (srm_bit(nzbits, (size_t)cy * n + cx)) { rx = cx; ry = cy; }
+            }
+            np = srm_pack(rx, ry);
+        }
+        if (shared_update) {
+            // newpos lives behind the accumulator pair of every rank (one IPC mapping covers both)
+            for (int q = 0; q < peers.world; ++q)
+                reinterpret_cast<int *>(const_cast<double *>(peers.acc[q]) + 2 * peers.stride)[id] = np;
+        } else {
+            newpos[id] = np;
+            if (np != SRM_SENT) srm_hash_claim(claim, (unsigned)np, id);
+        }
+    }
+    if (shared_update) {   // the last block to finish publishes this rank's slice
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            s_last = atomicAdd(&ctl->pos_ticket, 1) == (int)gridDim.x - 1;
+        }
+        __syncthreads();
+        if (s_last && (int)threadIdx.x < peers.world) {
+            if (threadIdx.x == 0) ctl->pos_ticket = 0;
+            const int target = (ctl->epoch << 20) | (ctl->it + 1);
+            __threadfence_system();
+            *(volatile int *)(peers.flags[threadIdx.x] + 64 + peers.rank) = target;
+        }
+    }
+}
+
+// Row bands with the fused all-reduce: claims of ALL sites, once every rank's slice of newpos has arrived.
+__global__ void k_update_claim(const int *newpos, SrmCtl *ctl, SrmHash claim, int respect_stop, SrmPeers peers) {
+    srm_pdl_enter();
+    if (respect_stop && ctl->stop) return;
+    if (threadIdx.x == 0) wait_flags(peers.flags_local + 64, peers.world, (ctl->epoch << 20) | (ctl->it + 1), ctl);
+    __syncthreads();
+    if (ctl->p2p_timeout) return;
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= ctl->K) return;
-    const int p = sites[id];
-    if (p == SRM_SENT) { newpos[id] = SRM_SENT; return; }
-    const int tx = srm_x(p), ty = srm_y(p);
-    int rx = tx, ry = ty;
-    if (!(maskbits && srm_bit(maskbits, (size_t)ty * n + tx))) {
-        double sW = 0, sX = 0, sY = 0;
-        if (peers.world > 1) {
-            // every rank marks the sites it contributed to (one byte per site, behind its accumulators): a site's
-            // cell spans one or two bands, so only those ranks' sums are pulled over NVLink.  Remote loads cost
-            // ~2 us each, so they are issued in independent batches of 8 ranks (all "touched" bytes, then all sums)
-            // and added in rank order (the same order on every rank: bit-identical totals).
-            for (int q0 = 0; q0 < peers.world; q0 += 8) {
-                const double *base[8];
-                unsigned char tch[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int q = min(q0 + k, peers.world - 1);
-                    base[k] = peers.acc[q] + (size_t)peers.parity * peers.stride;
-                    tch[k] = (q0 + k < peers.world)
-                                 ? __ldcv(reinterpret_cast<const unsigned char *>(base[k] + 4 * (size_t)peers.kcap + 4) + id)
-                                 : (unsigned char)0;
-                }
-                double2 wx[8];
-                double yy[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    wx[k] = make_double2(0, 0); yy[k] = 0;
-                    if (tch[k]) {
-                        const double *a = base[k] + 4 * (size_t)id;
-                        wx[k] = __ldcv(reinterpret_cast<const double2 *>(a));
-                        yy[k] = __ldcv(a + 2);
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (tch[k]) { sW += wx[k].x; sX += wx[k].y; sY += yy[k]; }
-            }
-        } else {
-            const double *a = acc + 4 * (size_t)id;
-            sW = a[0]; sX = a[1]; sY = a[2];
-        }
-        const float pW = (float)sW, pX = (float)sX, pY = (float)sY;
-        const float omega = ctl->omega;
-        const float _x = __fdiv_rn(pX, pW), _y = __fdiv_rn(pY, pW);
-        const float fx = __fadd_rn(__fmaf_rn(__fsub_rn(_x, (float)tx), omega, (float)tx), 0.5f);
-        const float fy = __fadd_rn(__fmaf_rn(__fsub_rn(_y, (float)ty), omega, (float)ty), 0.5f);
-        int cx = __float2int_rz(fx), cy = __float2int_rz(fy);  // NaN -> 0, like F2I.TRUNC
-        cx = max(min(cx, n - 1), 0);
-        cy = max(min(cy, n - 1), 0);
-        if (srm_bit(nzbits, (size_t)cy * n + cx)) { rx = cx; ry = cy; }
-    }
-    const int np = srm_pack(rx, ry);
-    newpos[id] = np;
-    srm_hash_claim(claim, (unsigned)np, id);
+    const int np = ld_volatile_int(newpos + id);   // written by peers: not through the read-only path
+    if (np != SRM_SENT) srm_hash_claim(claim, (unsigned)np, id);
 }
 
 #define UPD_NT 256
@@ -331,10 +382,26 @@ void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, dou
                        int want_energy, int stop_rule, int respect_stop, SrmPeers peers) {
     // acc: single GPU: the accumulator buffer; peers: the BASE of this rank's buffer pair
     const int k1 = Kcap > 0 ? Kcap : 1;
-    srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, nzbits, maskbits, g.n, ctl,
-                   newpos, s.hash_next, respect_stop, peers);
+    if (peers.world > 1 && peers.owner) {   // owner computes its slice of the ids, then every rank claims all of them
+        const int slice = k1 / peers.world + 1;
+        srm_launch_pdl(st, dim3((slice + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, nzbits, maskbits, g.n,
+                       ctl, newpos, s.hash_next, respect_stop, peers);
+        srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_claim, (const int *)newpos, ctl, s.hash_next, respect_stop, peers);
+    } else
+        srm_launch_pdl(st, dim3((k1 + 255) / 256), dim3(256), 0, k_update_pos, sites_in, (const double *)acc, nzbits, maskbits, g.n, ctl,
+                       newpos, s.hash_next, respect_stop, peers);
     srm_launch_pdl(st, dim3((k1 + UPD_NT - 1) / UPD_NT), dim3(UPD_NT), 0, k_update_resolve, (const int *)newpos, s.hash_next, g.n, g.row0,
                    g.row1, s.bits_next, s.edge_next, ctl, sites_out, acc, Kcap, want_energy, stop_rule, respect_stop, peers);
+}
+
+void srm_preload_kernels() {
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, k_update_pos);
+    cudaFuncGetAttributes(&a, k_update_claim);
+    cudaFuncGetAttributes(&a, k_update_resolve);
+    cudaFuncGetAttributes(&a, k_signal);
+    cudaFuncGetAttributes(&a, k_acc);
+    cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ multires (coarse-to-fine, gcvt.cu:485-511)

@@ -13,7 +13,7 @@ is CudaBandEngine over libsrm.so.
 """
 import numpy as np
 
-from .api import Context, row_bands
+from .api import Context, row_bands, scan_mask, scan_site_map
 
 
 class _CudaArray:
@@ -57,11 +57,37 @@ class CudaBandEngine:
         self.torch.cuda.current_stream(self.device).synchronize()
         for q, (a, b) in enumerate(bands):
             dist.broadcast(nz[a * n // 32: b * n // 32], src=q)
-        self.ctx.set_mask(mask)
-        self.ctx.set_site_map(site_map)
+        # the two sparse inputs: every rank scans ITS rows on the host; the lists of all ranks, concatenated in rank
+        # order, are the row-major scan of the whole arrays (the order a single GPU sees, so the site ids agree)
+        sites = scan_site_map(np.asarray(site_map).reshape(n, n, 2)[r0:r1])      # multi-threaded C scans (srm_host.cu)
+        mpx = scan_mask(mask, n, r0, r1) if mask is not None else np.zeros(0, np.int32)
+        sites, mpx = self._allgather_lists(dist, [sites, mpx], len(bands))
+        if mask is not None:
+            self.ctx.set_mask_pixels(mpx)
+        else:
+            self.ctx.set_mask(None)
+        self.ctx.set_sites(sites)
         ptr, cnt = self.ctx.acc_buffer()
         self._keep = _CudaArray(ptr, cnt)
         self._acc = self.torch.as_tensor(self._keep, device=self.device)
+
+    def _allgather_lists(self, dist, lists, world):
+        """Concatenation over the ranks (in rank order) of each of `lists` (int32 vectors of different lengths)."""
+        torch = self.torch
+        cnt = torch.tensor([len(a) for a in lists], dtype=torch.int64, device=self.device)
+        allc = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        allc = torch.stack(allc).cpu().numpy()            # [world, len(lists)]
+        out = []
+        for j, a in enumerate(lists):
+            m = int(allc[:, j].max())
+            buf = torch.zeros(max(m, 1), dtype=torch.int32, device=self.device)
+            if len(a):
+                buf[:len(a)] = torch.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            parts = [torch.zeros_like(buf) for _ in range(world)]
+            dist.all_gather(parts, buf)
+            out.append(np.concatenate([parts[q][:int(allc[q, j])].cpu().numpy() for q in range(world)]).astype(np.int32))
+        return out
 
     def set_sites(self, packed):
         self.ctx.set_sites(packed)
