@@ -299,7 +299,7 @@ def run_ours(args):
         # all ranks together: the density once (each rank its rows), the site / constraint lists on every rank
         h2d = (dens.nbytes + world * (4 * (k + nmask) + 4 * nmask)) / e2e_iters
         d2h = world * lab.nbytes / e2e_iters
-        eng.close()
+        sl.shutdown()
 
     # ---- BASELINE.json configs[3] (32768^2, 10^6 sites), time-boxed: device-resident steps only
     c4 = None
@@ -381,13 +381,35 @@ def run_c4(args, world, rank, local, dist):
     dens, mask, vor = make_inputs(n, k, pinned=False)
     nmask = int(mask.sum())
     bands = S.row_bands_balanced(n, world, np.nonzero(vor[..., 0] != -32768)[0]) if args.bands == "balanced" else S.row_bands(n, world)
-    r0, r1 = bands[rank]
-    eng = CudaBandEngine(n, r0, r1, local)
-    sl = ShardedLloyd(n, rank, world, eng, dist, bands)
-    sl.set_inputs(dens, mask, vor)
+
+    def build(bands_):
+        r0_, r1_ = bands_[rank]
+        eng_ = CudaBandEngine(n, r0_, r1_, local)
+        sl_ = ShardedLloyd(n, rank, world, eng_, dist, bands_)
+        sl_.set_inputs(dens, mask, vor)
+        if world > 1 and args.collective != "py":
+            sl_.bind_native_collective(args.collective)
+        return eng_, sl_
+
+    eng, sl = build(bands)
+    rebalanced_from = None
+    if world > 1 and args.c4_bands == "auto" and args.collective != "py":
+        # one round of measured rebalancing: band-kernel time of every rank on equal bands -> bands of equal cost
+        sl.run(3)
+        st0 = eng.ctx.iterate_profiled(6, stop_rule=False)
+        tb = torch.tensor([st0["band_fused"] / 6], device="cuda", dtype=torch.float64)
+        allt = [torch.zeros_like(tb) for _ in range(world)]
+        dist.all_gather(allt, tb)
+        times = [float(x.item()) for x in allt]
+        new_bands = S.rebalance_bands(bands, times)
+        if new_bands != bands:
+            rebalanced_from = {"bands": [b[1] - b[0] for b in bands], "k_band_ms_per_rank": [round(x, 4) for x in times]}
+            sl.shutdown()
+            bands = new_bands
+            eng, sl = build(bands)
+        else:
+            sl.set_inputs(dens, mask, vor)   # same partition: restart from the seeds (the hash counts iterations)
     del dens, vor
-    if world > 1 and args.collective != "py":
-        sl.bind_native_collective(args.collective)
     t_setup = time.time() - t0
 
     def barrier():
@@ -424,7 +446,9 @@ def run_c4(args, world, rank, local, dist):
            "k_band_ms_per_rank": band_ms, "stages_ms_per_step_rank0": {s_: round(v / 10, 4) for s_, v in stage.items()},
            "sites_sha1_after": {"steps": W + K + 10, "sha1": sites_sha1(sites)},
            "setup_s": round(t_setup, 1)}
-    eng.close()
+    if rebalanced_from:
+        out["rebalanced_from"] = rebalanced_from
+    sl.shutdown()
     del mask
     return out
 
@@ -537,6 +561,9 @@ def main():
     ap.add_argument("--c4-steps", dest="c4_steps", type=int, default=30,
                     help="timed steps of the BASELINE configs[3] leg (32768^2, 10^6 sites) appended to the line as `c4`; 0 = skip")
     ap.add_argument("--only-c4", dest="only_c4", action="store_true", help="run only the configs[3] leg")
+    ap.add_argument("--c4-bands", dest="c4_bands", default="auto", choices=["auto", "fixed"],
+                    help="configs[3] leg at N > 1: auto = one round of measured rebalancing of the row bands (default); "
+                         "fixed = the partition --bands gives")
     ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl", "py"],
                     help="N>1: p2p = fused all-reduce over peer memory inside the update kernel (default); nccl = NCCL "
                          "all-reduce issued by libsrm; py = torch.distributed all-reduce per step from Python")

@@ -156,6 +156,9 @@ int srm_nccl_init(srm_ctx *ctx, const char *id128, int rank, int world);
  * arrival flags and pulls the per-site partial sums from their memory over NVLink; no collective kernel runs. */
 int srm_p2p_info(srm_ctx *ctx, void *blob160);
 int srm_p2p_connect(srm_ctx *ctx, const void *blobs /* world x 160 bytes */, int rank, int world);
+/* Closes the mappings of the peers' buffers.  Every rank disconnects, the caller synchronises the ranks (barrier), and
+ * only then are the contexts destroyed: a mapping must not outlive the peer's buffer. */
+int srm_p2p_disconnect(srm_ctx *ctx);
 
 /* iters x (label, accumulate, update) with the reference's energy/omega schedule; stop_rule != 0
  * honours the reference stopping rule (checked on device; remaining iterations become no-ops). */

@@ -22,11 +22,12 @@ from .api import (  # noqa: F401
     recover,
     row_bands,
     row_bands_balanced,
+    rebalance_bands,
 )
 from .batch import BatchLloyd, shard_meshes  # noqa: F401
 
 __all__ = [
     "MARKER", "Context", "SrmError", "centroidalVoronoi", "discretization_d", "gCVT", "generateMask",
-    "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands", "row_bands_balanced",
+    "lib", "lib_path", "locate", "putConstrains", "randomPoints", "recover", "row_bands", "row_bands_balanced", "rebalance_bands",
     "BatchLloyd", "shard_meshes",
 ]

@@ -411,6 +411,19 @@ extern "C" int srm_p2p_connect(srm_ctx *c, const void *blobs, int rank, int worl
     return SRM_OK;
 }
 
+// Undo srm_p2p_connect: closes the mappings of the peers' buffers.  Collective in the sense that every rank must have
+// disconnected (caller: barrier) before any rank destroys its context — a peer's mapping must not outlive the buffer.
+extern "C" int srm_p2p_disconnect(srm_ctx *c) {
+    if (!c) return fail(SRM_ERR_ARG, "srm_p2p_disconnect: null ctx");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (void *p : c->ipc_opened) cudaIpcCloseMemHandle(p);
+    c->ipc_opened.clear();
+    c->p2p = false; c->world = c->comm ? c->world : 1; c->rank = 0;
+    drop_graphs(c);
+    return SRM_OK;
+}
+
 // A row band (not the whole grid) updates from partial sums unless a collective is bound: refuse instead of diverging.
 static int require_collective(srm_ctx *c, const char *who) {
     if (c->p2p || c->comm) return SRM_OK;

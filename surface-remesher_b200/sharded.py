@@ -186,6 +186,13 @@ class ShardedLloyd:
         self.native = True
         return True
 
+    def shutdown(self):
+        """Collective teardown of the band contexts: close the peer mappings on every rank, meet, then free."""
+        if getattr(self, "native", False) and self.world > 1 and hasattr(self.engine, "ctx"):
+            self.engine.ctx.p2p_disconnect()
+            self.dist.barrier()
+        self.engine.close()
+
     def run(self, iters):
         if getattr(self, "native", False) or (self.world == 1 and hasattr(self.engine, "ctx")):
             self.engine.ctx.iterate(iters, stop_rule=False)   # fused band kernel (+ NCCL all-reduce) + update, in C++
