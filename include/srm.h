@@ -184,6 +184,10 @@ int srm_get_labels(srm_ctx *ctx, short *out, int on_device);
 /* Alternative labelling (north_star kernel family, NOT the reference's algorithm): jump flooding with
  * the given step schedule on the current sites, whole-grid contexts only; result as dense labels. */
 int srm_label_jfa(srm_ctx *ctx, const int *steps, int nsteps, short *out, int on_device);
+/* Measurement: runs the same schedule with CUDA events between the launches.  mode 1 = fused shared-memory tile kernel
+ * for runs of small steps (sum <= 15) + vectorised far passes (the default of srm_label_jfa, option "jfa_mode"),
+ * mode 0 = one plain kernel per pass.  ms[i] = device milliseconds of launch i, *nlaunch = launches issued. */
+int srm_label_jfa_timed(srm_ctx *ctx, const int *steps, int nsteps, int mode, float *ms, int cap, int *nlaunch);
 
 #ifdef __cplusplus
 }

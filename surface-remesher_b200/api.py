@@ -88,10 +88,11 @@ def lib():
     L.srm_debug_get.argtypes = [p, i, C.POINTER(C.c_longlong)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
+    L.srm_label_jfa_timed.argtypes = [p, p, i, i, p, i, C.POINTER(i)]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
                  "srm_set_density_band", "srm_set_mask_pixels", "srm_scan_site_map_host", "srm_scan_mask_host", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_p2p_disconnect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
                  "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
-                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa"):
+                 "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa", "srm_label_jfa_timed"):
         getattr(L, name).restype = i
     _lib = L
     return L
@@ -497,6 +498,16 @@ class Context:
         p, dev = _ptr(out)
         _ck(lib().srm_label_jfa(self._h, st.ctypes.data_as(C.c_void_p), len(st), p, dev))
         return out
+
+    def label_jfa_timed(self, steps, mode=1):
+        """Measurement: device milliseconds of every launch of the schedule (mode 1: runs of small steps are one fused
+        shared-memory tile launch; mode 0: one plain kernel per pass)."""
+        st = np.ascontiguousarray(steps, np.int32)
+        ms = np.zeros(len(st), np.float32)
+        nl = C.c_int()
+        _ck(lib().srm_label_jfa_timed(self._h, st.ctypes.data_as(C.c_void_p), len(st), int(mode),
+                                      ms.ctypes.data_as(C.c_void_p), len(ms), C.byref(nl)))
+        return ms[:nl.value].astype(float).tolist()
 
 
 def unpack_sites(packed):

@@ -118,6 +118,8 @@ struct srm_ctx {
     SrmHash hash[2];           // pixel -> site id (and the dedupe claims of the update)
     int dbg_stats = 0;
     bool robust_only = false;  // option: label every row with the robust path (tests pin it this way)
+    int jfa_mode = 1;          // option: 1 = srm_jfa.cu (fused small-step tile kernel + vectorised far passes), 0 = one round-1
+                               // kernel per pass (A/B baseline), 3 = like 1 with the large-grid (n > 16384) instantiations
     // option "graph": srm_iterate replays a captured CUDA graph of 10 iterations (the period of the loop: buffer
     // parity 2, energy every 10th) instead of launching 50 kernels from the host — for launch-bound sizes / batches
     bool use_graph = false;
@@ -750,6 +752,7 @@ extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
     if (!c || !name) return fail(SRM_ERR_ARG, "srm_set_option: null argument");
     if (!strcmp(name, "robust_only")) { c->robust_only = value != 0; return SRM_OK; }
     if (!strcmp(name, "graph")) { c->use_graph = value != 0; return SRM_OK; }
+    if (!strcmp(name, "jfa_mode")) { c->jfa_mode = value & 3; return SRM_OK; }
     if (!strcmp(name, "dbg_stats")) {
         c->dbg_stats = value;
         CK(cudaStreamSynchronize(c->stream));
@@ -1132,29 +1135,55 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
     return SRM_OK;
 }
 
-extern "C" int srm_label_jfa(srm_ctx *c, const int *steps, int nsteps, short *out, int on_device) {
-    int rc = require_ready(c, "srm_label_jfa", false);
+// Seeds the dense map `a` from the site list and runs the JFA schedule between a and b (srm_jfa.cu); *res = the buffer
+// that holds the labels.
+static int jfa_run(srm_ctx *c, const char *who, const int *steps, int nsteps, int mode, int **res, cudaEvent_t *ev, int evcap,
+                   int *nlaunch) {
+    int rc = require_ready(c, who, false);
     if (rc) return rc;
     rc = resync(c);
     if (rc) return rc;
-    if (!steps || nsteps <= 0 || !out) return fail(SRM_ERR_ARG, "srm_label_jfa: bad argument");
-    if (c->g.row0 != 0 || c->g.row1 != c->g.n) return fail(SRM_ERR_ARG, "srm_label_jfa: whole-grid contexts only");
+    if (!steps || nsteps <= 0) return fail(SRM_ERR_ARG, "%s: bad argument", who);
+    if (c->g.row0 != 0 || c->g.row1 != c->g.n) return fail(SRM_ERR_ARG, "%s: whole-grid contexts only", who);
+    for (int s = 0; s < nsteps; ++s)
+        if (steps[s] <= 0 || steps[s] >= c->g.n) return fail(SRM_ERR_ARG, "%s: step %d", who, steps[s]);
     CK(cudaSetDevice(c->device));
     if (!c->labels) CK(cudaMalloc(&c->labels, c->N * sizeof(int)));
     if (!c->scratch_map) CK(cudaMalloc(&c->scratch_map, c->N * sizeof(int)));
-    int *a = c->scratch_map, *b = c->labels;
-    srm_launch_fill_int(c->stream, a, c->N, SRM_SENT);
-    srm_launch_scatter_sites(c->stream, c->sites[current_buffer(c)], c->ctl, c->Kcap, c->g.n, a);
-    for (int s = 0; s < nsteps; ++s) {
-        if (steps[s] <= 0) return fail(SRM_ERR_ARG, "srm_label_jfa: step %d", steps[s]);
-        srm_launch_jfa_pass(c->stream, a, b, c->g.n, steps[s]);
-        std::swap(a, b);
-    }
-    CK(cudaGetLastError());
+    srm_launch_fill_int(c->stream, c->scratch_map, c->N, SRM_SENT);
+    srm_launch_scatter_sites(c->stream, c->sites[current_buffer(c)], c->ctl, c->Kcap, c->g.n, c->scratch_map);
+    cudaError_t e = cudaSuccess;
+    *res = srm_launch_jfa(c->stream, c->scratch_map, c->labels, c->g.n, steps, nsteps, mode, ev, evcap, nlaunch, &e);
+    CK(e);
+    return SRM_OK;
+}
+
+extern "C" int srm_label_jfa(srm_ctx *c, const int *steps, int nsteps, short *out, int on_device) {
+    if (!out) return fail(SRM_ERR_ARG, "srm_label_jfa: bad argument");
+    int *a = nullptr;
+    int rc = jfa_run(c, "srm_label_jfa", steps, nsteps, c ? c->jfa_mode : 0, &a, nullptr, 0, nullptr);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(out, a, c->N * sizeof(int), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
                        c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return SRM_OK;
+}
+
+// Measurement: the same schedule with an event between the launches; ms[i] = device time of launch i (a fused run of
+// small steps is one launch).  The labels stay on the device (srm_label_jfa returns them).
+extern "C" int srm_label_jfa_timed(srm_ctx *c, const int *steps, int nsteps, int mode, float *ms, int cap, int *nlaunch) {
+    if (!ms || !nlaunch || cap <= 0) return fail(SRM_ERR_ARG, "srm_label_jfa_timed: bad argument");
+    std::vector<cudaEvent_t> ev((size_t)nsteps + 1, nullptr);
+    for (auto &x : ev) CK(cudaEventCreate(&x));
+    int *a = nullptr, nl = 0;
+    int rc = jfa_run(c, "srm_label_jfa_timed", steps, nsteps, mode, &a, ev.data(), (int)ev.size(), &nl);
+    if (rc == SRM_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) rc = fail(SRM_ERR_CUDA, "srm_label_jfa_timed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == SRM_OK) {
+        *nlaunch = nl;
+        for (int i = 0; i < nl && i < cap; ++i) cudaEventElapsedTime(&ms[i], ev[(size_t)i], ev[(size_t)i + 1]);
+    }
+    for (auto &x : ev) cudaEventDestroy(x);
+    return rc;
 }
 
 // ------------------------------------------------------------------ one-shot drop-ins

@@ -248,6 +248,9 @@ void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, i
                                int *blockoff, int *total_out, int count_only);
 void srm_launch_scan_counts(cudaStream_t st, const int *cnt, int *off, int nb, int *total_out);
 void srm_launch_jfa_pass(cudaStream_t st, const int *in, int *out, int n, int step);
+// whole JFA schedule between two dense maps (srm_jfa.cu); returns the buffer holding the result
+int *srm_launch_jfa(cudaStream_t st, int *a, int *b, int n, const int *steps, int nsteps, int fused, cudaEvent_t *ev,
+                    int evcap, int *nlaunch, cudaError_t *err);
 void srm_launch_scatter_sites(cudaStream_t st, const int *sites, const SrmCtl *ctl, int Kcap, int n, int *map);
 void srm_launch_fill_int(cudaStream_t st, int *p, size_t count, int value);
 // multires (gcvt.cu:485-511): 2x2 box filter of the density (s = output side), site zoom x2

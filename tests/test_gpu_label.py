@@ -107,12 +107,16 @@ def test_label_unequal_row_bands(n, bands):
         assert (got != exp[r0:r1]).sum() == 0
 
 
-def test_jfa_matches_cpu_jfa_and_error_rate():
+@pytest.mark.parametrize("mode", [0, 1, 3])
+def test_jfa_matches_cpu_jfa_and_error_rate(mode):
+    """mode 0: one plain kernel per pass; 1: srm_jfa.cu (fused shared-memory tile kernel for runs of small steps +
+    vectorised far passes, the default); 3: the same with the n > 16384 instantiations (explicit empty-label test)."""
     import surface_remesher_b200 as S
     n = 512
     seeds = I.random_sites(n, 2000, 12)
     steps = [1] + [n >> (i + 1) for i in range(int(np.log2(n)))]  # 1+JFA
     with S.Context(n) as c:
+        c.set_option("jfa_mode", mode)
         c.set_site_map(np.ascontiguousarray(seeds))
         got = c.label_jfa(steps)
     exp = O.label_jfa(seeds, steps)
@@ -123,6 +127,45 @@ def test_jfa_matches_cpu_jfa_and_error_rate():
     d_e = (exact[..., 0].astype(np.int64) - xs) ** 2 + (exact[..., 1].astype(np.int64) - ys) ** 2
     assert (d_j < d_e).sum() == 0           # JFA can never beat the exact distance
     assert (d_j > d_e).mean() < 1e-3        # and is wrong on well under 0.1 % of pixels
+
+
+def _jfa_case(case, n):
+    if case == "lattice":      # thousands of exact ties: the (x, y) part of the key decides
+        seeds = np.full((n, n, 2), I.MARK, np.int16)
+        for yy in range(3, n, 10):
+            for xx in range(5, n, 10):
+                seeds[yy, xx] = (xx, yy)
+        return seeds, [n // 4, 16, 6, 5, 2, 1, 1]          # far (vector), tile [6, 5, 2, 1], tile [1]
+    if case == "border":       # sites only on the grid's edge and corners; steps that are not multiples of 4
+        seeds = np.full((n, n, 2), I.MARK, np.int16)
+        for q in range(0, n, 17):
+            seeds[0, q] = (q, 0); seeds[n - 1, q] = (q, n - 1); seeds[q, 0] = (0, q); seeds[q, n - 1] = (n - 1, q)
+        seeds[n - 1, n - 1] = (n - 1, n - 1)
+        return seeds, [3, 101, 50, 27, 13, 7, 3, 1]        # tile [3], far (scalar), tile [13], tile [7, 3, 1]
+    if case == "one":          # a single site: most pixels stay empty through the early passes
+        seeds = np.full((n, n, 2), I.MARK, np.int16)
+        seeds[n - 56, 13] = (13, n - 56)
+        return seeds, [4, 2, 1, 8, 4, 2, 1, n // 2, 2, 2, 2, 2, 2]
+    seeds = I.random_sites(n, 5000, 77)
+    return seeds, [1] + [n >> (i + 1) for i in range(int(np.log2(n)))] + [2, 1]   # 1+JFA+2
+
+
+@pytest.mark.parametrize("mode", [0, 1, 3])
+@pytest.mark.parametrize("case", ["lattice", "border", "one", "random"])
+def test_jfa_schedules_bit_exact_vs_cpu_jfa(case, mode):
+    """Arbitrary schedules (fused runs of every length, scalar and vector far passes, ties, empty regions, sites on the
+    border) against the CPU JFA of the same schedule and key."""
+    import surface_remesher_b200 as S
+    n = 1024 if case == "random" else 512
+    seeds, steps = _jfa_case(case, n)
+    with S.Context(n) as c:
+        c.set_option("jfa_mode", mode)
+        c.set_site_map(np.ascontiguousarray(seeds))
+        got = c.label_jfa(steps)
+        ms = c.label_jfa_timed(steps, mode)
+    assert (got != O.label_jfa(seeds, steps)).sum() == 0
+    # one launch per pass in mode 0; runs of small steps are single launches otherwise
+    assert (len(ms) == len(steps) if mode == 0 else 0 < len(ms) < len(steps)) and all(t >= 0 for t in ms)
 
 
 def test_no_sites_and_single_site():
