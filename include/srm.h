@@ -178,6 +178,19 @@ long long srm_launch_count(void);
  * band-list length, 2 bands, 6 warps that took the staging-overflow fallback of Phase A. */
 int srm_debug_get(srm_ctx *ctx, int which, long long *value);
 
+/* Host side of the boundary: worker threads (1..16, 0 = default: SRM_HOST_THREADS or half the hardware threads, at most
+ * 8) of the pageable <-> device copy pipeline and of the host scans of the seed map and the mask; staging chunk size in
+ * KB (256..65536, 0 = unchanged, default 4096). */
+int srm_host_config(int threads, int chunk_kb);
+
+/* Measurement / A-B tests: process-wide choice between two builds of a streaming kernel.  which = "expand" (runs ->
+ * dense labels) or "prefix" (fp64 prefix sums); value 0 / 1, < 0 = environment (SRM_EXPAND_V, SRM_PREFIX_V) / default. */
+int srm_set_variant(const char *which, int value);
+
+/* Measurement: device milliseconds per launch of a streaming kernel on the context's resident data (`reps` launches
+ * between two CUDA events after one untimed launch).  which = "prefix" (density set) or "expand" (after srm_label). */
+int srm_time_kernel(srm_ctx *ctx, const char *which, int reps, float *ms_per_launch);
+
 /* Dense labels of this band (rows row0..row1): expands the run-length labels of the last srm_label.
  * out: (row1-row0)*n short2. */
 int srm_get_labels(srm_ctx *ctx, short *out, int on_device);

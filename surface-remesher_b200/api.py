@@ -88,6 +88,12 @@ def lib():
     L.srm_debug_get.argtypes = [p, i, C.POINTER(C.c_longlong)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
+    L.srm_set_variant.argtypes = [C.c_char_p, i]
+    L.srm_host_config.argtypes = [i, i]
+    L.srm_host_config.restype = i
+    L.srm_time_kernel.argtypes = [p, C.c_char_p, i, C.POINTER(C.c_float)]
+    L.srm_time_kernel.restype = i
+    L.srm_set_variant.restype = i
     L.srm_label_jfa_timed.argtypes = [p, p, i, i, p, i, C.POINTER(i)]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
                  "srm_set_density_band", "srm_set_mask_pixels", "srm_scan_site_map_host", "srm_scan_mask_host", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_p2p_disconnect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
@@ -499,6 +505,12 @@ class Context:
         _ck(lib().srm_label_jfa(self._h, st.ctypes.data_as(C.c_void_p), len(st), p, dev))
         return out
 
+    def time_kernel(self, which, reps=10):
+        """Measurement: device ms per launch of a streaming kernel ("prefix" / "expand") on the resident data."""
+        ms = C.c_float()
+        _ck(lib().srm_time_kernel(self._h, which.encode(), int(reps), C.byref(ms)))
+        return ms.value
+
     def label_jfa_timed(self, steps, mode=1):
         """Measurement: device milliseconds of every launch of the schedule (mode 1: runs of small steps are one fused
         shared-memory tile launch; mode 0: one plain kernel per pass)."""
@@ -508,6 +520,16 @@ class Context:
         _ck(lib().srm_label_jfa_timed(self._h, st.ctypes.data_as(C.c_void_p), len(st), int(mode),
                                       ms.ctypes.data_as(C.c_void_p), len(ms), C.byref(nl)))
         return ms[:nl.value].astype(float).tolist()
+
+
+def host_config(threads=0, chunk_kb=0):
+    """Worker threads / staging chunk size of the pageable-copy pipeline and the host scans (0 = default / unchanged)."""
+    _ck(lib().srm_host_config(int(threads), int(chunk_kb)))
+
+
+def set_variant(which, value):
+    """Measurement / A-B tests: process-wide choice between two builds of a streaming kernel ("expand", "prefix")."""
+    _ck(lib().srm_set_variant(which.encode(), int(value)))
 
 
 def unpack_sites(packed):

@@ -763,6 +763,24 @@ extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
     return fail(SRM_ERR_ARG, "srm_set_option: unknown option %s", name);
 }
 
+// Tuning of the host side of the boundary (srm_host.cu): worker threads of the pageable-copy pipeline and of the host
+// scans (1..16, 0 = default), staging chunk size in KB (256..65536, 0 = unchanged).
+extern "C" int srm_host_config(int threads, int chunk_kb) {
+    if (srm_host_set_config(threads, chunk_kb)) return fail(SRM_ERR_ARG, "srm_host_config: threads %d / chunk %d KB out of range", threads, chunk_kb);
+    return SRM_OK;
+}
+
+// Process-wide choice between two builds of a streaming kernel (measurement tools and A/B tests): which = "expand"
+// (runs -> dense labels: 0 one binary search per 4-pixel group, 1 two-level lookup) or "prefix" (fp64 prefix sums:
+// 0 128/64-bit stores, 1 256-bit stores); value < 0 = back to the environment / compiled default.
+extern int g_srm_expand_v, g_srm_prefix_v;
+extern "C" int srm_set_variant(const char *which, int value) {
+    if (!which) return fail(SRM_ERR_ARG, "srm_set_variant: null argument");
+    if (!strcmp(which, "expand")) { g_srm_expand_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
+    if (!strcmp(which, "prefix")) { g_srm_prefix_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
+    return fail(SRM_ERR_ARG, "srm_set_variant: unknown kernel %s", which);
+}
+
 // Site extraction in the order delaunayInput scans the label map (delaunay.h:46-57: x outer, y inner; sites are
 // pixels with label == self that are not constraint pixels; point = (x*scale + l, y*scale + b)).  The reference
 // downloads the 2N-short label map and scans it on the host; here the K-entry site list is read back instead.
@@ -1132,6 +1150,30 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
         else CK(srm_d2h_pageable(out, dst, NB * sizeof(int), c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
+    return SRM_OK;
+}
+
+// Measurement: device milliseconds per launch of one of the two streaming kernels on this context's resident data, `reps`
+// launches between two events.  which = "prefix" (needs the density) or "expand" (needs a labelling with run-length rows).
+extern "C" int srm_time_kernel(srm_ctx *c, const char *which, int reps, float *ms_per_launch) {
+    if (!c || !which || reps <= 0 || !ms_per_launch) return fail(SRM_ERR_ARG, "srm_time_kernel: bad argument");
+    CK(cudaSetDevice(c->device));
+    const bool prefix = !strcmp(which, "prefix");
+    if (!prefix && strcmp(which, "expand")) return fail(SRM_ERR_ARG, "srm_time_kernel: unknown kernel %s", which);
+    if (prefix && !c->has_density) return fail(SRM_ERR_STATE, "srm_time_kernel: density not set");
+    if (!prefix && !c->labelled) return fail(SRM_ERR_STATE, "srm_time_kernel: call srm_label first");
+    if (!prefix && !c->labels) CK(cudaMalloc(&c->labels, (size_t)c->g.nrows() * c->g.n * sizeof(int)));
+    for (int i = -1; i < reps; ++i) {   // one untimed launch first
+        if (i == 0) CK(cudaEventRecord(c->ev0, c->stream));
+        if (prefix) srm_launch_prefix(c->stream, c->density, c->g, c->P2, c->PXX);
+        else CK(srm_launch_expand(c->stream, rle_of(c), c->g, c->labels));
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    CK(cudaGetLastError());
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_per_launch = ms / (float)reps;
     return SRM_OK;
 }
 

@@ -278,5 +278,6 @@ cudaError_t srm_d2h_pageable(void *dst_host, const void *src_dev, size_t bytes, 
 void srm_scan_site_map(const int *site_map, size_t N, std::vector<int> &sites);
 void srm_scan_mask(const unsigned char *mask, int n, std::vector<int> &pixels, int row0 = 0, int row1 = -1);
 void srm_host_pool_release();
+int srm_host_set_config(int threads, int chunk_kb);
 void srm_launch_scatter_mask(cudaStream_t st, const int *pixels, int count, int n, uint32_t *maskbits);
 #endif

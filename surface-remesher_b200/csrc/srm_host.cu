@@ -20,8 +20,9 @@
 
 namespace {
 
-constexpr size_t CHUNK = 4u << 20;
-constexpr int MAX_T = 8;
+constexpr int MAX_T = 16;
+size_t CHUNK = 4u << 20;   // staging buffer size; srm_host_config() may change it (the pool is rebuilt)
+int g_threads = 0;         // 0 = default: SRM_HOST_THREADS or half the hardware threads, at most 8
 
 struct Lane {   // per worker thread: two pinned staging buffers, a stream, an event per buffer
     void *pin[2] = {nullptr, nullptr};
@@ -36,12 +37,12 @@ std::mutex g_mu;
 Pool g_pool;
 
 int pool_threads() {
-    static const int t = []() {
+    static const int dflt = []() {
         const char *e = getenv("SRM_HOST_THREADS");
-        int v = e ? atoi(e) : (int)std::thread::hardware_concurrency() / 2;
+        int v = e ? atoi(e) : std::min(8, (int)std::thread::hardware_concurrency() / 2);
         return std::max(1, std::min(MAX_T, v));
     }();
-    return t;
+    return g_threads > 0 ? g_threads : dflt;
 }
 
 // (re)creates the staging buffers for the current device; returns cudaSuccess or the first error
@@ -83,6 +84,18 @@ void parallel(int T, F f) {
 }
 
 }  // namespace
+
+// Measurement / tuning: worker threads (1..16, 0 = default) and staging chunk size in KB (256..65536, 0 = keep) of the
+// pageable-copy pipeline and the host scans.  The staging pool is rebuilt on the next copy.
+void srm_host_pool_release();
+int srm_host_set_config(int threads, int chunk_kb) {
+    if (threads < 0 || threads > MAX_T || (chunk_kb != 0 && (chunk_kb < 256 || chunk_kb > 65536))) return -1;
+    srm_host_pool_release();
+    std::lock_guard<std::mutex> lock(g_mu);
+    g_threads = threads;
+    if (chunk_kb) CHUNK = (size_t)chunk_kb << 10;
+    return 0;
+}
 
 void srm_host_pool_release() {
     std::lock_guard<std::mutex> lock(g_mu);

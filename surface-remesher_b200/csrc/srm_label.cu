@@ -15,6 +15,7 @@
 // All arithmetic is integer; ties follow the reference (column tie: gcvt.cu:97-119 + :172-216;
 // row tie -> smallest x: gcvt.cu:449-466).
 #include "srm_common.cuh"
+#include <stdlib.h>
 #include "srm_envelope.cuh"
 #include <algorithm>
 
@@ -498,8 +499,74 @@ __global__ void __launch_bounds__(EXP_NT) k_expand(SrmRle R, int n, int *__restr
     }
 }
 
+// Two-level form: the binary search is done once per block of 32 pixels (n / 32 searches per row instead of n / 4), the
+// result kept in shared memory; a group of 4 pixels starts from its block's run and walks forward (runs are ~26 pixels
+// long: one or two steps).  The round-2 kernel above spends ~100 instructions and a chain of ~12 dependent shared-memory
+// loads per group, which is what bounds it (2.6 TB/s against a 7.1 TB/s write-only stream, profiles/r2_stream_peaks.json).
+#define EXP2_CAP 2048   // runs of a row staged in shared memory (16 KB)
+__global__ void __launch_bounds__(EXP_NT) k_expand2(SrmRle R, int n, int *__restrict__ labels) {
+    __shared__ __align__(16) int2 s_runs2[EXP2_CAP];
+    __shared__ int s_lo[1024];   // n / 32 <= 1024
+    __shared__ __align__(8) unsigned long long bar;
+    const int r = blockIdx.x, t = threadIdx.x;
+    if (R.off[r] < 0) return;   // the pool was exhausted: the host repeats the labelling with a larger one
+    const int cnt = R.cnt[r];
+    const int2 *runs = R.pool + R.off[r];
+    int4 *out = reinterpret_cast<int4 *>(labels + (size_t)r * n);
+    if (cnt == 0) {   // no site at all
+        for (int q = t; q < (n >> 2); q += EXP_NT) out[q] = make_int4(SRM_SENT, SRM_SENT, SRM_SENT, SRM_SENT);
+        return;
+    }
+    if (cnt <= EXP2_CAP) {
+        if (t == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (t == 0) bulk_load(s_runs2, runs, (unsigned)(((cnt + 1) & ~1) * sizeof(int2)), &bar);
+        mbar_wait(&bar, 0);
+        runs = s_runs2;
+    }
+    for (int b = t; b < (n >> 5); b += EXP_NT) {
+        const int x = b << 5;
+        int lo = 0, hi = cnt;   // largest e with start(e) <= x; start(0) == 0
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (runs[mid].y <= x) lo = mid; else hi = mid;
+        }
+        s_lo[b] = lo;
+    }
+    __syncthreads();
+    auto start = [&](int e) { return e < cnt ? runs[e].y : INT_MAX; };
+    for (int q = t; q < (n >> 2); q += EXP_NT) {
+        const int x = q << 2;
+        int e = s_lo[x >> 5];
+        int nxt = start(e + 1);
+        while (nxt <= x) { ++e; nxt = start(e + 1); }
+        int lab = runs[e].x;
+        int4 v;
+        v.x = lab;
+        while (nxt <= x + 1) { ++e; lab = runs[e].x; nxt = start(e + 1); }
+        v.y = lab;
+        while (nxt <= x + 2) { ++e; lab = runs[e].x; nxt = start(e + 1); }
+        v.z = lab;
+        while (nxt <= x + 3) { ++e; lab = runs[e].x; nxt = start(e + 1); }
+        v.w = lab;
+        out[q] = v;
+    }
+}
+
+#ifndef SRM_EXPAND_DEFAULT
+#define SRM_EXPAND_DEFAULT 0
+#endif
+// 1 = two-level k_expand2, 0 = k_expand (A/B baseline).  SRM_EXPAND_V in the environment (read once) or
+// srm_set_variant("expand", v) (measurement tools) override the compiled default.
+int g_srm_expand_v = -1;
+static int expand_variant() {
+    if (g_srm_expand_v < 0) { const char *e = getenv("SRM_EXPAND_V"); g_srm_expand_v = e ? atoi(e) != 0 : SRM_EXPAND_DEFAULT; }
+    return g_srm_expand_v;
+}
+
 cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels) {
-    SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, EXP_CAP * sizeof(int2), st>>>(rle, g.n, labels);
+    if (expand_variant()) SRM_COUNT(), k_expand2<<<g.nrows(), EXP_NT, 0, st>>>(rle, g.n, labels);
+    else SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, EXP_CAP * sizeof(int2), st>>>(rle, g.n, labels);
     return cudaGetLastError();
 }
 

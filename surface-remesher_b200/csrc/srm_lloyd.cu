@@ -12,10 +12,23 @@
 #include "srm_common.cuh"
 #include "srm_envelope.cuh"
 #include <algorithm>
+#include <stdlib.h>
+
+#ifndef SRM_PREFIX_DEFAULT
+#define SRM_PREFIX_DEFAULT 0
+#endif
 
 // ------------------------------------------------------------------ prefix sums (once per call)
 
 #define PFX_NT 256
+// 256-bit global stores (sm_100+: STG.E.ENL2.256): a thread's four consecutive prefix entries leave as full 32-byte
+// sectors (P2: two stores of two double2 each, PXX: one store) instead of four 16-byte and four 8-byte partial-sector
+// stores that L2 has to merge.
+__device__ __forceinline__ void st_global_256(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <bool WIDE>
 __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ density, int n, double2 *__restrict__ P2,
                                                    double *__restrict__ PXX) {
     __shared__ double sw[3][PFX_NT / 32];
@@ -53,10 +66,17 @@ __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ den
         }
         if (in) {
             const size_t o = srm_pfx_row(r, n) + (size_t)x * SRM_PFX_TILE;   // tiled layout, srm_common.cuh
+            if (WIDE && SRM_PFX_TILE == 1) {
+                double *p2 = reinterpret_cast<double *>(P2 + o);   // 64-byte aligned: x is a multiple of 4
+                st_global_256(p2, ew + W[0], ex + X[0], ew + W[1], ex + X[1]);
+                st_global_256(p2 + 4, ew + W[2], ex + X[2], ew + W[3], ex + X[3]);
+                st_global_256(PXX + o, exx + XX[0], exx + XX[1], exx + XX[2], exx + XX[3]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                P2[o + (size_t)k * SRM_PFX_TILE] = make_double2(ew + W[k], ex + X[k]);
-                PXX[o + (size_t)k * SRM_PFX_TILE] = exx + XX[k];
+                for (int k = 0; k < 4; ++k) {
+                    P2[o + (size_t)k * SRM_PFX_TILE] = make_double2(ew + W[k], ex + X[k]);
+                    PXX[o + (size_t)k * SRM_PFX_TILE] = exx + XX[k];
+                }
             }
         }
         cW += tw; cX += tx; cXX += txx;
@@ -64,8 +84,17 @@ __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ den
     }
 }
 
+// 1 = 256-bit stores, 0 = 128/64-bit stores (the round-1 form; A/B baseline).  SRM_PREFIX_V in the environment (read
+// once) or srm_set_variant("prefix", v) (measurement tools) override the compiled default.
+int g_srm_prefix_v = -1;
+static int prefix_variant() {
+    if (g_srm_prefix_v < 0) { const char *e = getenv("SRM_PREFIX_V"); g_srm_prefix_v = e ? atoi(e) != 0 : SRM_PREFIX_DEFAULT; }
+    return g_srm_prefix_v;
+}
+
 void srm_launch_prefix(cudaStream_t st, const float *density_band, SrmGrid g, double2 *P2, double *PXX) {
-    SRM_COUNT(), k_prefix<<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
+    if (prefix_variant()) SRM_COUNT(), k_prefix<true><<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
+    else SRM_COUNT(), k_prefix<false><<<g.nrows(), PFX_NT, 0, st>>>(density_band, g.n, P2, PXX);
 }
 
 // ------------------------------------------------------------------ per-run accumulation

@@ -132,6 +132,21 @@ def test_argument_errors_locate_recover():
     assert L.srm_recover(*args(None, None, 2)) == 1                       # more constraint points than points
 
 
+def test_tuning_entry_points_validate_their_arguments():
+    """srm_host_config / srm_set_variant need no device: range and name checks, and back to the defaults."""
+    import surface_remesher_b200 as S
+    S.api.host_config(4, 1024)
+    S.api.host_config(16, 65536)
+    for bad in [(17, 0), (-1, 0), (4, 100), (4, 1 << 20)]:
+        with pytest.raises(S.SrmError, match="out of range"):
+            S.api.host_config(*bad)
+    S.api.host_config(0, 4096)
+    S.api.set_variant("expand", 1); S.api.set_variant("prefix", 1)
+    S.api.set_variant("expand", -1); S.api.set_variant("prefix", -1)
+    with pytest.raises(S.SrmError, match="unknown kernel"):
+        S.api.set_variant("band", 1)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""The two streaming kernels of a gCVT call on the headline grid, both builds of each (srm_set_variant):
+k_prefix (4 B/px read, 24 B/px written; 0 = 128/64-bit stores, 1 = 256-bit stores) and k_expand (4 B/px written from
+~20 MB of runs; 0 = binary search per 4-pixel group, 1 = two-level lookup), device time per launch from CUDA events
+(srm_time_kernel: 20 launches after one untimed), as GB/s against the measured copy and write-only stream rates.
+
+    python tools/bench_streams.py [--n 8192] [--sites 100000] > gpurun_out/streams.json
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench                      # noqa: E402
+import surface_remesher_b200 as S  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=8192)
+    ap.add_argument("--sites", type=int, default=100000)
+    a = ap.parse_args()
+    n = a.n
+    dens, mask, vor = bench.make_inputs(n, a.sites, pinned=False)
+    peak, src = bench.measured_peaks()
+    out = {"grid": n, "sites": a.sites, "copy_peak_GBs": peak, "peak_source": src}
+    sp = os.path.join(ROOT, "profiles", "r2_stream_peaks.json")
+    if os.path.exists(sp):
+        out["write_only_peak_GBs"] = json.load(open(sp))["write_only_fill_GBs"]
+    N = n * n
+    with S.Context(n) as c:
+        c.set_density(dens); c.set_mask(mask); c.set_site_map(vor)
+        c.iterate(20, stop_rule=False)   # Lloyd-relaxed sites: the run structure of a real final labelling
+        c.label()
+        runs, _ = c.debug_counts()
+        out["runs"] = int(runs)
+        for v in (0, 1):
+            S.api.set_variant("prefix", v); S.api.set_variant("expand", v)
+            tp = min(c.time_kernel("prefix", 20) for _ in range(3))
+            te = min(c.time_kernel("expand", 20) for _ in range(3))
+            out[f"variant{v}"] = {
+                "k_prefix_ms": tp, "k_prefix_GBs": 28.0 * N / tp / 1e6, "k_prefix_frac_of_copy_peak": 28.0 * N / tp / 1e6 / peak,
+                "k_expand_ms": te, "k_expand_GBs": (4.0 * N + 8.0 * runs) / te / 1e6,
+                "k_expand_frac_of_copy_peak": (4.0 * N + 8.0 * runs) / te / 1e6 / peak}
+        S.api.set_variant("prefix", -1); S.api.set_variant("expand", -1)
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()
