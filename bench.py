@@ -96,25 +96,73 @@ def make_inputs(n, k, pinned):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU while the timed region runs.  The timed region of the default run is a
+    few milliseconds, shorter than one `nvidia-smi -lms` period, so the samples are taken in-process through NVML by a
+    thread (~1 kHz; the main thread waits in cudaStreamSynchronize with the GIL released); `nvidia-smi -lms 100` runs
+    beside it as a fallback.  mark_begin() / mark_end() bracket the timed region: "sm_mhz" is the median of the samples
+    inside it (or, if it was too short for any, of the samples since the warm-up started)."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NVML_REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.nv, self.nv_stop, self.nv_thread, self.nv_max = [], False, None, None
+        self.t_begin = self.t_end = None
+
+    def _nvml_handle(self):
+        import pynvml as N
+        N.nvmlInit()
+        try:   # CUDA_VISIBLE_DEVICES may renumber the devices: go through the UUID
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            return N, N.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            return N, N.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _nvml_loop(self, N, h):
+        while not self.nv_stop:
+            try:
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                try:
+                    rs = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.nv.append((time.perf_counter(), float(sm), int(rs)))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        try:
+            N, h = self._nvml_handle()
+            self.nv_max = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            self.nv_thread = threading.Thread(target=self._nvml_loop, args=(N, h), daemon=True)
+            self.nv_thread.start()
+        except Exception as e:
+            log("[bench] NVML clock sampling unavailable:", e)
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception as e:  # nvidia-smi missing
-            log("[bench] clock sampling unavailable:", e)
+            log("[bench] nvidia-smi clock sampling unavailable:", e)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        self.nv_stop = True
+        if self.nv_thread:
+            self.nv_thread.join(timeout=1.0)
         if self.proc:
             time.sleep(0.15)
             self.proc.terminate()
@@ -122,8 +170,20 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [nm for j, nm in enumerate(names) if any(len(r) > 3 + j and r[3 + j].startswith("Active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": reasons, "samples": len(sm), "source": "nvidia-smi -lms 100"}
+        if self.nv:
+            inside = [x for x in self.nv if self.t_begin is not None and self.t_end is not None and self.t_begin <= x[0] <= self.t_end]
+            use = inside if inside else self.nv
+            bits = 0
+            for x in use:
+                bits |= x[2]
+            out = {"sm_mhz": float(np.median([x[1] for x in use])), "sm_max_mhz": self.nv_max or out["sm_max_mhz"],
+                   "reasons": sorted(set(reasons) | {nm for b, nm in self.NVML_REASONS.items() if bits & b}),
+                   "samples": len(use), "samples_in_timed_region": len(inside),
+                   "source": "NVML, in-process thread" + ("" if inside else " (timed region shorter than one sample: warm-up + timed region)"),
+                   "nvidia_smi_samples": len(sm)}
+        return out
 
 
 def sites_sha1(packed):
@@ -207,17 +267,19 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident timing: W warm-up steps, then exactly K steps between events
-    sl.run(W)
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    sl.run(W)
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = launches()
+    sampler.mark_begin()
     e0.record()
     sl.run(K)
     e1.record()
     barrier()
+    sampler.mark_end()
     gpu_launches = launches() - l0          # kernels of libsrm launched by this rank inside the timed region
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None

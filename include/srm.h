@@ -178,6 +178,13 @@ long long srm_launch_count(void);
  * band-list length, 2 bands, 6 warps that took the staging-overflow fallback of Phase A. */
 int srm_debug_get(srm_ctx *ctx, int which, long long *value);
 
+/* Option "band_order" (srm_set_option; default: SRM_BAND_ORDER in the environment, else the compiled default): the CTAs
+ * of the band kernel take the 8-row bands by decreasing cost — runs per band of an earlier iteration, rebuilt on the
+ * device every 10th iteration — instead of in row order, so that the last wave of CTAs is made of the cheap bands.
+ * Results do not depend on it.  This returns the order (perm_out[i] = band of CTA i) and the cost per band of the last
+ * labelling; *num_bands = rows / 8; nothing is written when capacity < *num_bands. */
+int srm_debug_band_order(srm_ctx *ctx, int *perm_out, int *cost_out, int capacity, int *num_bands);
+
 /* Host side of the boundary: worker threads (1..16, 0 = default: SRM_HOST_THREADS or half the hardware threads, at most
  * 8) of the pageable <-> device copy pipeline and of the host scans of the seed map and the mask; staging chunk size in
  * KB (256..65536, 0 = unchanged, default 4096). */

@@ -86,6 +86,7 @@ def lib():
     L.srm_get_state.argtypes = [p, p]
     L.srm_debug_counts.argtypes = [p, C.POINTER(C.c_longlong), C.POINTER(i)]
     L.srm_debug_get.argtypes = [p, i, C.POINTER(C.c_longlong)]
+    L.srm_debug_band_order.argtypes = [p, p, p, i, C.POINTER(i)]
     L.srm_get_labels.argtypes = [p, p, i]
     L.srm_label_jfa.argtypes = [p, p, i, p, i]
     L.srm_set_variant.argtypes = [C.c_char_p, i]
@@ -488,6 +489,15 @@ class Context:
         v = C.c_longlong()
         _ck(lib().srm_debug_get(self._h, int(which), C.byref(v)))
         return v.value
+
+    def debug_band_order(self):
+        """(perm, cost): the band kernel's CTA -> band order (option "band_order") and the runs per 8-row band of the
+        last labelling, from which the order is rebuilt every 10th iteration."""
+        nb = C.c_int()
+        _ck(lib().srm_debug_band_order(self._h, None, None, 0, C.byref(nb)))
+        perm = np.empty(nb.value, np.int32); cost = np.empty(nb.value, np.int32)
+        _ck(lib().srm_debug_band_order(self._h, _ptr(perm)[0], _ptr(cost)[0], nb.value, C.byref(nb)))
+        return perm, cost
 
     def get_labels(self, out=None):
         rows = self.row1 - self.row0

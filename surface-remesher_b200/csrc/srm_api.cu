@@ -86,6 +86,15 @@ static int load_nccl() {
     return SRM_OK;
 }
 
+// Default of the option "band_order" (SRM_BAND_ORDER=0/1 overrides it; read once per process).
+static int default_band_order() {
+    static const int v = []() {
+        const char *e = getenv("SRM_BAND_ORDER");
+        return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : SRM_BAND_ORDER_DEFAULT;
+    }();
+    return v;
+}
+
 struct srm_ctx {
     SrmGrid g{};
     int device = 0;
@@ -114,6 +123,10 @@ struct srm_ctx {
     int rle_cap = 0;
     int *rle_cnt = nullptr, *rle_off = nullptr, *labels = nullptr, *scratch_map = nullptr;
     int *ovf_rows = nullptr;   // rows the band kernel hands to the robust path
+    // option "band_order": the band kernel's CTAs take the bands by decreasing cost (runs per band of an earlier
+    // iteration, srm_band.cu "Band order") instead of in row order; the permutation is rebuilt every 10th iteration
+    int *band_perm = nullptr;
+    int band_order = default_band_order();
     int *edge[2] = {nullptr, nullptr};   // row bands: per column, nearest site row above / below the band (2n ints)
     SrmHash hash[2];           // pixel -> site id (and the dedupe claims of the update)
     int dbg_stats = 0;
@@ -142,6 +155,9 @@ struct srm_ctx {
     int **d_peer_flags = nullptr;
     std::vector<void *> ipc_opened;
 };
+
+// CTA -> band permutation of the band kernel, or nullptr for row order
+static const int *perm_of(const srm_ctx *c) { return c->band_order ? c->band_perm : nullptr; }
 
 static void drop_graphs(srm_ctx *c) {
     for (int i = 0; i < 2; ++i) if (c->graph[i]) { cudaGraphExecDestroy(c->graph[i]); c->graph[i] = nullptr; }
@@ -273,6 +289,13 @@ extern "C" int srm_create(srm_ctx **out, int n, int row0, int row1, int device) 
     CKD(cudaMalloc(&c->rle, (size_t)c->rle_cap * sizeof(int2)));
     CKD(cudaMalloc(&c->row_scratch, (size_t)srm_row_scratch_ctas(c->g.nrows()) * n * sizeof(int2)));
     CKD(cudaMalloc(&c->rle_cnt, (size_t)c->g.nrows() * sizeof(int)));
+    CKD(cudaMemsetAsync(c->rle_cnt, 0, (size_t)c->g.nrows() * sizeof(int), c->stream));
+    {   // band order: the identity until the first rebuild
+        std::vector<int> ident((size_t)c->g.nrows() / 8);
+        for (size_t i = 0; i < ident.size(); ++i) ident[i] = (int)i;
+        CKD(cudaMalloc(&c->band_perm, ident.size() * sizeof(int)));
+        CKD(cudaMemcpy(c->band_perm, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     CKD(cudaMalloc(&c->rle_off, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ovf_rows, (size_t)c->g.nrows() * sizeof(int)));
     CKD(cudaMalloc(&c->ctl, sizeof(SrmCtl)));
@@ -301,7 +324,7 @@ extern "C" int srm_destroy(srm_ctx *c) {
     if (c->d_peer_acc) cudaFree((void *)c->d_peer_acc);
     if (c->d_peer_flags) cudaFree((void *)c->d_peer_flags);
     void *ptrs[] = {c->density, c->nzbits, c->maskbits, c->P2, c->PXX, c->sites[0], c->sites[1], c->acc, c->blockcnt,
-                    c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->row_scratch, c->rle_cnt, c->rle_off, c->ovf_rows,
+                    c->blockoff, c->bits_alloc[0], c->bits_alloc[1], c->up_alloc, c->dn_alloc, c->rle, c->row_scratch, c->rle_cnt, c->rle_off, c->ovf_rows, c->band_perm,
                     c->edge[0], c->edge[1], c->hash[0].b, c->hash[1].b, c->labels, c->scratch_map, c->ctl};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -747,12 +770,34 @@ extern "C" int srm_debug_get(srm_ctx *c, int which, long long *value) {
     return SRM_OK;
 }
 
+// Measurement / tests: the band kernel's CTA -> band order and the cost (runs per band of the last labelling) it is rebuilt from.
+extern "C" int srm_debug_band_order(srm_ctx *c, int *perm_out, int *cost_out, int capacity, int *num_bands) {
+    if (!c || !num_bands) return fail(SRM_ERR_ARG, "srm_debug_band_order: null argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    const int nb = c->g.nrows() / 8;
+    *num_bands = nb;
+    if (capacity < nb) return SRM_OK;
+    if (perm_out) CK(cudaMemcpy(perm_out, c->band_perm, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost));
+    if (cost_out) {
+        std::vector<int> h((size_t)c->g.nrows());
+        CK(cudaMemcpy(h.data(), c->rle_cnt, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int b = 0; b < nb; ++b) {
+            int sum = 0;
+            for (int r = 0; r < 8; ++r) sum += std::min(std::max(h[(size_t)b * 8 + r], 0), 32767);
+            cost_out[b] = sum;
+        }
+    }
+    return SRM_OK;
+}
+
 // Options: "robust_only" (0/1): label with the worst-case-capacity row path only (no fused band kernel).
 extern "C" int srm_set_option(srm_ctx *c, const char *name, int value) {
     if (!c || !name) return fail(SRM_ERR_ARG, "srm_set_option: null argument");
     if (!strcmp(name, "robust_only")) { c->robust_only = value != 0; return SRM_OK; }
     if (!strcmp(name, "graph")) { c->use_graph = value != 0; return SRM_OK; }
     if (!strcmp(name, "jfa_mode")) { c->jfa_mode = value & 3; return SRM_OK; }
+    if (!strcmp(name, "band_order")) { c->band_order = value != 0; drop_graphs(c); return SRM_OK; }
     if (!strcmp(name, "dbg_stats")) {
         c->dbg_stats = value;
         CK(cudaStreamSynchronize(c->stream));
@@ -839,7 +884,10 @@ static int band_flags(srm_ctx *c, int respect_stop, int accumulate, int want_ene
 }
 
 // write_rle: the run-length rows are needed by srm_get_labels / srm_accumulate after this labelling (not inside the loop)
-static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy, int write_rle = 1) {
+// in_loop: an iteration of the Lloyd loop (the band order is rebuilt from the run counts of iteration it - 1 when
+// it % 10 == 1: the period of the captured graphs)
+static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int want_energy, int write_rle = 1,
+                      int in_loop = 0) {
     double *acc = cur_acc(c, it);
     const SrmStep s = step_of(c, it);
     srm_launch_carry(c->stream, s, c->g.n, c->up, c->dn, c->ctl, respect_stop, c->g.row0, c->g.row1);
@@ -847,7 +895,7 @@ static int label_with(srm_ctx *c, int it, int respect_stop, int accumulate, int 
     if (!c->robust_only) {
         CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), c->ovf_rows, c->P2, c->PXX,
                            s.hash, acc, c->Kcap, c->ctl, band_flags(c, respect_stop, accumulate, want_energy, write_rle),
-                           c->dbg_stats));
+                           c->dbg_stats, perm_of(c), in_loop && it % 10 == 1));
         rows = c->ovf_rows;
         count = &c->ctl->ovf;
     }
@@ -966,7 +1014,7 @@ extern "C" int srm_update(srm_ctx *c) {
 // One Lloyd iteration on the context's stream (the body of the loop at gcvt.cu:1112-1123).
 static int one_iteration(srm_ctx *c, int it, int stop_rule) {
     const int buf = it & 1, want_energy = (it % 10) == 0;
-    int rc = label_with(c, it, 1, 1, want_energy, /*write_rle=*/0);
+    int rc = label_with(c, it, 1, 1, want_energy, /*write_rle=*/0, /*in_loop=*/1);
     if (rc) return rc;
     rc = allreduce_acc(c);  // no-op for a single band and in peer-memory mode
     if (rc) return rc;
@@ -980,7 +1028,8 @@ static int one_iteration(srm_ctx *c, int it, int stop_rule) {
 // through "every 10th computes the energy", and the stop flag / iteration counter live on the device, so one graph
 // serves every block of ten.  Captured without the PDL attribute (plain kernel-to-kernel edges).
 static int capture_graph(srm_ctx *c, int stop_rule) {
-    const int key = (c->Kcap << 3) ^ (c->has_mask ? 1 : 0) ^ (c->robust_only ? 2 : 0) ^ (c->dbg_stats ? 4 : 0) ^ (c->p2p ? 0x40000000 : 0);
+    const int key = (c->Kcap << 3) ^ (c->has_mask ? 1 : 0) ^ (c->robust_only ? 2 : 0) ^ (c->dbg_stats ? 4 : 0) ^ (c->p2p ? 0x40000000 : 0) ^
+                    (c->band_order ? 0x20000000 : 0);
     if (key != c->graph_key) { drop_graphs(c); c->graph_key = key; }
     if (c->graph[stop_rule]) return SRM_OK;
     cudaGraph_t g = nullptr;
@@ -1063,7 +1112,8 @@ extern "C" int srm_iterate_profiled(srm_ctx *c, int iters, int stop_rule, float 
         const int *rows = nullptr, *count = nullptr;
         if (!c->robust_only) {
             CK(srm_launch_band(c->stream, s.bits, c->up, c->dn, c->g, rle_of(c), c->ovf_rows, c->P2, c->PXX,
-                               s.hash, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats));
+                               s.hash, acc, c->Kcap, c->ctl, band_flags(c, 1, 1, want_energy, 0), c->dbg_stats, perm_of(c),
+                               it % 10 == 1));
             rows = c->ovf_rows;
             count = &c->ctl->ovf;
         }

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
                                                   SrmRle rle, int *ovf_rows,
                                                   const double2 *__restrict__ P2, const double *__restrict__ PXX,
                                                   SrmHash hash, double *__restrict__ acc, int Kcap,
-                                                  SrmCtl *ctl, int flags, int dbg) {
+                                                  SrmCtl *ctl, int flags, int dbg, const int *__restrict__ perm) {
     constexpr int R = BAND_NW * RPW;
     static_assert(R <= 16, "in-band bits are packed in 16 bits");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -288,7 +288,9 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
 
     const int t = threadIdx.x, lane = t & 31, w = t >> 5;
     double e_loc = 0;
-    const int bi = blockIdx.x;
+    // CTA -> band: in launch order, or (band order, below) the bands that were the most expensive in an earlier
+    // iteration first, so that the last wave of CTAs is made of the cheap ones
+    const int bi = perm ? perm[blockIdx.x] : (int)blockIdx.x;
     const int rb = bi * R, Y0 = row0 + rb, j = Y0 >> 5, k0 = Y0 & 31;
     const size_t wrow = (size_t)j * n;
     const int nb = n >> 3;
@@ -600,6 +602,49 @@ __global__ void __launch_bounds__(BAND_NT, BAND_MINCTA) k_band(const uint32_t *_
     }
 }
 
+// ---- Band order.  The grid of k_band is 1.7 waves of CTAs at the headline sizes (1024 bands for 592 resident CTAs at
+// 8192^2; 512 for 296 on each of 8 GPUs at 32768^2) and a band's cost varies 2.7x with the local site density (C3: 1430
+// to 3850 runs per band), so in launch order the expensive middle bands start in the second wave and the kernel ends
+// with a long tail of half-empty SMs.  Longest-processing-time-first: the bands are issued by decreasing cost of an
+// EARLIER iteration (runs per band, which k_band records per row anyway; sites move a few pixels per iteration, so the
+// cost profile is stable), and the tail is made of the cheap bands.  List-scheduling model on the measured run counts
+// (tools/sim_band_order.py): makespan -13 %.  The order is a hint: any permutation gives the same results.
+//
+// k_band_order: one CTA; key = cost << 12 | (4095 - band) sorted in decreasing order by a bitonic network in shared
+// memory (equal costs keep the launch order; an all-equal profile, e.g. before the first iteration, is the identity).
+#define BAND_ORDER_MAX 4096   // bands of one context: rows / 8 <= 32768 / 8
+#define BAND_ORDER_NT 1024
+__global__ void __launch_bounds__(BAND_ORDER_NT) k_band_order(const int *__restrict__ cnt, int nb, int R, int *__restrict__ perm) {
+    __shared__ int key[BAND_ORDER_MAX];
+    srm_pdl_enter();
+    const int t = threadIdx.x;
+    int P = 1;
+    while (P < nb) P <<= 1;
+    for (int i = t; i < P; i += BAND_ORDER_NT) {
+        int k = -1;   // padding sorts last
+        if (i < nb) {
+            int s = 0;
+            for (int r = 0; r < R; ++r) s += min(max(cnt[i * R + r], 0), 32767);
+            k = (min(s, (1 << 18) - 1) << 12) | (BAND_ORDER_MAX - 1 - i);
+        }
+        key[i] = k;
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = t; i < P; i += BAND_ORDER_NT) {
+                const int q = i ^ j;
+                if (q > i) {
+                    const int a = key[i], b = key[q];
+                    const bool desc = (i & k) == 0;
+                    if ((a < b) == desc) { key[i] = b; key[q] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = t; i < nb; i += BAND_ORDER_NT) perm[i] = BAND_ORDER_MAX - 1 - (key[i] & (BAND_ORDER_MAX - 1));
+}
+
 // Per-warp element buffer (entries of 4 B): must hold a row's envelope + 62 (and, when accumulating, one 1024 / 1280-byte
 // stage of the prefix ring).  Rows of an n-wide grid with the BASELINE site densities have ~n/26 runs (316 at
 // 8192^2/100k, 520 at 16384^2/250k, 950 at 32768^2/1M).
@@ -659,21 +704,25 @@ static int band_rpw(int nrows) {
 template <int RPW, int C>
 static void band_launch_one(cudaStream_t st, size_t smem, const uint32_t *bits, const short *up, const short *dn, SrmGrid g,
                             int CL, SrmRle rle, int *ovf_rows, const double2 *P2, const double *PXX,
-                            SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
+                            SrmHash hash, double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg, const int *perm) {
     const int nbands = g.nrows() / (BAND_NW * RPW);
     srm_launch_pdl(st, dim3(nbands), dim3(BAND_NT), smem, k_band<RPW, C>, bits, up, dn, g.n, g.row0, CL, rle, ovf_rows, P2,
-                   PXX, hash, acc, Kcap, ctl, flags, dbg);
+                   PXX, hash, acc, Kcap, ctl, flags, dbg, perm);
 }
 
 int srm_band_bufcap(int n) { return band_bufcap(n); }
 
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
                             int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
-                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg) {
+                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg, const int *perm, int refresh_order) {
     const int CL = band_cap(g.n);
     const size_t smem = band_smem(g.n, CL);
     const int rpw = band_rpw(g.nrows()), C = band_bufcap(g.n);
-#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, ovf_rows, P2, PXX, hash, acc, Kcap, ctl, flags, dbg
+    if (perm && refresh_order) {
+        const int R = BAND_NW * rpw;
+        srm_launch_pdl(st, dim3(1), dim3(BAND_ORDER_NT), 0, k_band_order, (const int *)rle.cnt, g.nrows() / R, R, const_cast<int *>(perm));
+    }
+#define BAND_ARGS st, smem, bits, up, dn, g, CL, rle, ovf_rows, P2, PXX, hash, acc, Kcap, ctl, flags, dbg, perm
     if (C == BAND_C8K) { if (rpw == 1) band_launch_one<1, BAND_C8K>(BAND_ARGS); else band_launch_one<2, BAND_C8K>(BAND_ARGS); }
     else if (C == 1280) { if (rpw == 1) band_launch_one<1, 1280>(BAND_ARGS); else band_launch_one<2, 1280>(BAND_ARGS); }
     else { if (rpw == 1) band_launch_one<1, 1792>(BAND_ARGS); else band_launch_one<2, 1792>(BAND_ARGS); }

@@ -5,6 +5,9 @@
 #include <limits.h>
 
 #define SRM_MARK (-32768)
+#ifndef SRM_BAND_ORDER_DEFAULT
+#define SRM_BAND_ORDER_DEFAULT 0   // default of the option "band_order" (srm_band.cu "Band order"; environment SRM_BAND_ORDER)
+#endif
 #define SRM_TIE_BAND_SHIFT 6   // 64-row bands of the reference's phase 1 (n/m1 == 64, gcvt.cu:842-847)
 #define SRM_BIG 40000          // "no site in this column" distance; > any real |dy| (<= 32767), BIG^2+225 < 2^31
 #define SRM_SENT ((int)0x80008000)  // (MARK,MARK) packed
@@ -220,7 +223,8 @@ enum {
 };
 cudaError_t srm_launch_band(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
                             int *ovf_rows, const double2 *P2, const double *PXX, SrmHash hash,
-                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg = 0);
+                            double *acc, int Kcap, SrmCtl *ctl, int flags, int dbg = 0, const int *perm = nullptr,
+                            int refresh_order = 0);   // perm: CTA -> band order (srm_band.cu "Band order"), rebuilt first if asked
 // robust path, driven by a row list (rows == nullptr: every row of the band)
 cudaError_t srm_launch_row(cudaStream_t st, const uint32_t *bits, const short *up, const short *dn, SrmGrid g, SrmRle rle,
                            const int *rows, const int *count, const double2 *P2, const double *PXX,
