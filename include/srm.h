@@ -140,6 +140,14 @@ int srm_label(srm_ctx *ctx);                       /* pba2DCompute: exact labels
 int srm_accumulate(srm_ctx *ctx, int want_energy); /* pbaCVDComputeCentroid (+pbaCVDCalcEnergy): per-site sums over this band */
 int srm_update(srm_ctx *ctx);                      /* pbaCVDUpdateSites + the control block of gcvt.cu:1123-1140 */
 int srm_label_accumulate(srm_ctx *ctx, int want_energy); /* srm_label + srm_accumulate fused in one kernel pass */
+/* The centroid pass as a stand-alone streaming kernel over a DENSE label map (north_star's form; alternative to the fused
+ * accumulation of srm_label_accumulate, NOT used by the loop): per-site sums of this band from labels_dev — device
+ * memory, (row1-row0)*n short2, 16-byte aligned, e.g. the output of srm_get_labels / srm_label_jfa with on_device = 1;
+ * NULL = the labels of the last srm_label, expanded into the context's own dense buffer first — and the density:
+ * 8 B/px read once, warp-segmented reduction, one set of fp64 REDs per run.  Labels that are not live sites of the
+ * context are ignored.  Adds to the accumulators srm_accumulate fills.
+ * Replaces <- pbaCVDComputeCentroid gcvt.cu:1008-1023 (+ pbaCVDCalcEnergy gcvt.cu:1059-1083 with want_energy). */
+int srm_accumulate_dense(srm_ctx *ctx, const short *labels_dev, int want_energy);
 /* Device accumulators for an external all-reduce between srm_accumulate and srm_update:
  * 4*capacity+4 doubles: (W, X, Y, 0) per site, then (energy_sum,0,0,0). */
 int srm_acc_buffer(srm_ctx *ctx, void **device_ptr, size_t *num_doubles);
@@ -195,7 +203,9 @@ int srm_host_config(int threads, int chunk_kb);
 int srm_set_variant(const char *which, int value);
 
 /* Measurement: device milliseconds per launch of a streaming kernel on the context's resident data (`reps` launches
- * between two CUDA events after one untimed launch).  which = "prefix" (density set) or "expand" (after srm_label). */
+ * between two CUDA events after one untimed launch).  which = "prefix" (density set), "expand" (after srm_label),
+ * "centroid" / "centroid_energy" (srm_accumulate_dense on the context's own dense labels, after srm_label; the
+ * accumulators are cleared afterwards). */
 int srm_time_kernel(srm_ctx *ctx, const char *which, int reps, float *ms_per_launch);
 
 /* Dense labels of this band (rows row0..row1): expands the run-length labels of the last srm_label.

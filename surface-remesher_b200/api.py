@@ -77,6 +77,7 @@ def lib():
     L.srm_set_option.argtypes = [p, C.c_char_p, i]
     L.srm_label.argtypes = [p]
     L.srm_accumulate.argtypes = [p, i]
+    L.srm_accumulate_dense.argtypes = [p, p, i]
     L.srm_label_accumulate.argtypes = [p, i]
     L.srm_update.argtypes = [p]
     L.srm_acc_buffer.argtypes = [p, C.POINTER(p), C.POINTER(C.c_size_t)]
@@ -98,7 +99,7 @@ def lib():
     L.srm_label_jfa_timed.argtypes = [p, p, i, i, p, i, C.POINTER(i)]
     for name in ("srm_gcvt", "srm_release_cache", "srm_discretize", "srm_seed", "srm_generate_mask", "srm_locate", "srm_recover", "srm_create", "srm_destroy",
                  "srm_set_density_band", "srm_set_mask_pixels", "srm_scan_site_map_host", "srm_scan_mask_host", "srm_shared_bits", "srm_set_stream", "srm_nccl_unique_id", "srm_nccl_init", "srm_p2p_info", "srm_p2p_connect", "srm_p2p_disconnect", "srm_synchronize", "srm_set_density", "srm_set_mask", "srm_set_site_map",
-                 "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_label_accumulate", "srm_update",
+                 "srm_set_sites", "srm_get_sites", "srm_extract_sites", "srm_set_omega", "srm_set_option", "srm_label", "srm_accumulate", "srm_accumulate_dense", "srm_debug_band_order", "srm_label_accumulate", "srm_update",
                  "srm_acc_buffer", "srm_iterate", "srm_iterate_profiled", "srm_run", "srm_get_state", "srm_debug_counts", "srm_debug_get", "srm_get_labels", "srm_label_jfa", "srm_label_jfa_timed"):
         getattr(L, name).restype = i
     _lib = L
@@ -444,6 +445,16 @@ class Context:
     def accumulate(self, want_energy):
         _ck(lib().srm_accumulate(self._h, int(bool(want_energy))))
 
+    def accumulate_dense(self, labels=None, want_energy=False):
+        """Stand-alone centroid pass over a dense label map on the device (torch CUDA tensor of this band's rows, int16
+        [rows, n, 2]); None = the labels of the last label(), expanded into the context's own dense buffer first."""
+        ptr = None
+        if labels is not None:
+            ptr, on_dev = _ptr(labels)
+            if not on_dev:
+                raise TypeError("accumulate_dense: labels must be a device tensor")
+        _ck(lib().srm_accumulate_dense(self._h, ptr, int(bool(want_energy))))
+
     def label_accumulate(self, want_energy):
         _ck(lib().srm_label_accumulate(self._h, int(bool(want_energy))))
 
@@ -516,7 +527,8 @@ class Context:
         return out
 
     def time_kernel(self, which, reps=10):
-        """Measurement: device ms per launch of a streaming kernel ("prefix" / "expand") on the resident data."""
+        """Measurement: device ms per launch of a streaming kernel ("prefix" / "expand" / "centroid" / "centroid_energy")
+        on the resident data."""
         ms = C.c_float()
         _ck(lib().srm_time_kernel(self._h, which.encode(), int(reps), C.byref(ms)))
         return ms.value

@@ -981,6 +981,37 @@ extern "C" int srm_accumulate(srm_ctx *c, int want_energy) {
     return SRM_OK;
 }
 
+// The centroid pass in north_star's stand-alone form (srm_centroid.cu): per-site sums of this band from a DENSE label map
+// on the device and the density, one streaming pass.  labels_dev == nullptr: the run-length labels of the last srm_label
+// are expanded into the context's own dense buffer first (the reference's data flow: label map -> sums).  Adds to the
+// same accumulators as srm_accumulate; srm_update follows as usual.
+static int expand_own_labels(srm_ctx *c, const char *who) {
+    if (!c->labelled) return fail(SRM_ERR_STATE, "%s: call srm_label first (or pass a label map)", who);
+    if (!c->labels) CK(cudaMalloc(&c->labels, (size_t)c->g.nrows() * c->g.n * sizeof(int)));
+    CK(srm_launch_expand(c->stream, rle_of(c), c->g, c->labels));
+    return SRM_OK;
+}
+
+extern "C" int srm_accumulate_dense(srm_ctx *c, const short *labels_dev, int want_energy) {
+    int rc = require_ready(c, "srm_accumulate_dense", true);
+    if (rc) return rc;
+    rc = resync(c);
+    if (rc) return rc;
+    CK(cudaSetDevice(c->device));
+    const int *lab = reinterpret_cast<const int *>(labels_dev);
+    if (!lab) {
+        rc = expand_own_labels(c, "srm_accumulate_dense");
+        if (rc) return rc;
+        lab = c->labels;
+    }
+    if ((reinterpret_cast<uintptr_t>(lab) & 15) != 0) return fail(SRM_ERR_ARG, "srm_accumulate_dense: the label map must be 16-byte aligned");
+    CK(srm_launch_centroid_dense(c->stream, lab, c->density, c->hash[c->it_host & 1], c->g, cur_acc(c, c->it_host), c->Kcap,
+                                 want_energy, c->p2p ? 1 : 0));
+    srm_launch_signal(c->stream, c->ctl, peers_of(c, c->it_host), 0);
+    CK(cudaGetLastError());
+    return SRM_OK;
+}
+
 extern "C" int srm_acc_buffer(srm_ctx *c, void **device_ptr, size_t *num_doubles) {
     if (!c || !device_ptr || !num_doubles) return fail(SRM_ERR_ARG, "srm_acc_buffer: null argument");
     if (!c->has_sites) return fail(SRM_ERR_STATE, "srm_acc_buffer: sites not set");
@@ -1208,7 +1239,28 @@ extern "C" int srm_get_labels(srm_ctx *c, short *out, int on_device) {
 extern "C" int srm_time_kernel(srm_ctx *c, const char *which, int reps, float *ms_per_launch) {
     if (!c || !which || reps <= 0 || !ms_per_launch) return fail(SRM_ERR_ARG, "srm_time_kernel: bad argument");
     CK(cudaSetDevice(c->device));
-    const bool prefix = !strcmp(which, "prefix");
+    const bool prefix = !strcmp(which, "prefix"), centroid = !strcmp(which, "centroid") || !strcmp(which, "centroid_energy");
+    if (centroid) {   // the stand-alone centroid pass over this context's dense labels; the accumulators are cleared afterwards
+        if (!c->has_density || !c->has_sites) return fail(SRM_ERR_STATE, "srm_time_kernel: density / sites not set");
+        int rc = resync(c);
+        if (rc) return rc;
+        rc = expand_own_labels(c, "srm_time_kernel");
+        if (rc) return rc;
+        double *acc = cur_acc(c, c->it_host);
+        for (int i = -1; i < reps; ++i) {
+            if (i == 0) CK(cudaEventRecord(c->ev0, c->stream));
+            CK(srm_launch_centroid_dense(c->stream, c->labels, c->density, c->hash[c->it_host & 1], c->g, acc, c->Kcap,
+                                         !strcmp(which, "centroid_energy"), 0));
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaMemsetAsync(acc, 0, c->acc_stride * sizeof(double), c->stream));
+        CK(cudaEventSynchronize(c->ev1));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        *ms_per_launch = ms / (float)reps;
+        return SRM_OK;
+    }
     if (!prefix && strcmp(which, "expand")) return fail(SRM_ERR_ARG, "srm_time_kernel: unknown kernel %s", which);
     if (prefix && !c->has_density) return fail(SRM_ERR_STATE, "srm_time_kernel: density not set");
     if (!prefix && !c->labelled) return fail(SRM_ERR_STATE, "srm_time_kernel: call srm_label first");

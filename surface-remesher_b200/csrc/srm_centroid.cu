@@ -1,0 +1,114 @@
+// srm_centroid.cu — the centroid pass in north_star's stand-alone form: ONE streaming pass over a dense label map and the
+// density (8 B/px read, nothing per-pixel written), warp-level segmented reduction, one set of REDs per run segment.
+//
+// Reference counterpart: pbaCVDComputeCentroid (gcvt.cu:1008-1023 -> kernelComputeWeightedPrefix*, kernelTotal_X,
+// kernelScan_Y, gcvt.cu:514-732: fp32 prefix images + two reductions over the label map) and, with want_energy,
+// kernelCalcEnergy + kernelReduce (gcvt.cu:788-832, 1059-1083).
+//
+// NOT the product path.  The Lloyd loop never materialises labels: the band kernel (srm_band.cu) adds the fp64 prefix
+// differences of every run to its site while it still holds the run in shared memory, which
+// costs 22 us of REDs + 11 us of prefix fetches per iteration at 8192^2.  This kernel exists for callers that already
+// hold a dense label map (the jump-flooding family srm_label_jfa, external labellings), as the parity counterpart of
+// the reference's own data flow (labels -> sums), and as the measured answer to "what would a label-map centroid pass
+// cost at its roofline": 8 B/px * N streamed once.
+//
+// One warp = 128 consecutive pixels of one row (n is a multiple of 256, so a warp never straddles rows); a thread owns 4
+// pixels (one 128-bit load of labels, one of the density).  Threads whose 4 labels agree ("uniform", ~85 % at 26-pixel
+// runs) enter a segmented reduction over the warp: heads are the lanes whose label differs from their left neighbour's,
+// a lane adds its partner at distance o only if no head lies in between (read off the ballot of the heads), so
+// non-adjacent runs of one label (possible in approximate labellings) are never merged across the lanes between them,
+// and five shuffle steps leave every segment's (W, X) in its head lane.  Heads look the site id up in the pixel -> id hash and issue three fp64 REDs
+// (W, X, Y * W).  Threads that straddle a run boundary add their sub-runs directly.  North_star's "shared-memory
+// per-site accumulators": a shared-memory fp64 atomicAdd is a CAS loop (ATOMS.CAST.SPIN, ~64 cycles per warp
+// instruction), dearer than the global RED it would save (1.3 cycles per lane; profiles/r2_kernel_log.md), so the
+// per-warp segment sums go to global memory directly — one RED set per run and row, exactly what the band kernel issues.
+//
+// Sums are fp64 in tree order; the float the update law rounds them to is what the parity tests compare
+// (tests/test_gpu_centroid.py: per-site sums against the run-based kernel and the oracle's direct sums, the updated
+// sites bit-exact against the oracle's step).
+#include "srm_common.cuh"
+
+#define CEN_NT 256
+#define CEN_MINCTA 6
+
+__device__ __forceinline__ void cen_emit(int label, double W, double X, int Y, const SrmHash &hash, double *__restrict__ acc,
+                                         int Kcap, int touch) {
+    if (label == SRM_SENT) return;   // pixel without a site (empty site set)
+    const int id = srm_hash_find(hash, (unsigned)label);
+    if (id < 0) return;              // not a live site of this iteration (foreign label map): ignored
+    double *a = acc + 4 * (size_t)id;
+    atomicAdd(a, W);
+    atomicAdd(a + 1, X);
+    atomicAdd(a + 2, (double)Y * W);
+    if (touch) reinterpret_cast<unsigned char *>(acc + 4 * (size_t)Kcap + 4)[id] = 1;
+}
+
+__global__ void __launch_bounds__(CEN_NT, CEN_MINCTA)
+k_centroid_dense(const int4 *__restrict__ labels4, const float4 *__restrict__ dens4, SrmHash hash, int n, int row0, int nrows,
+                 double *__restrict__ acc, int Kcap, int want_energy, int touch) {
+    const int lane = threadIdx.x & 31;
+    const unsigned gpr = (unsigned)n >> 2;                               // 4-pixel groups per row (a multiple of 64)
+    const unsigned groups = (unsigned)nrows * gpr;                       // <= 32768 * 8192 = 2^28
+    const unsigned stride = gridDim.x * CEN_NT;
+    double e_loc = 0;
+    for (unsigned g = blockIdx.x * CEN_NT + threadIdx.x; g < groups; g += stride) {   // warp-uniform trip count
+        const int4 L = labels4[g];
+        const float4 D = dens4[g];
+        const unsigned r = g / gpr;
+        const int x0 = (int)(g - r * gpr) << 2, Y = row0 + (int)r;
+        const int lab[4] = {L.x, L.y, L.z, L.w};
+        const double d[4] = {(double)D.x, (double)D.y, (double)D.z, (double)D.w};
+        if (want_energy) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int dx = (int)(short)(lab[k] & 0xffff) - (x0 + k), dy = (lab[k] >> 16) - Y;
+                if (lab[k] != SRM_SENT) e_loc += d[k] * (double)(dx * dx + dy * dy);
+            }
+        }
+        const bool uni = lab[0] == lab[1] && lab[1] == lab[2] && lab[2] == lab[3];
+        double W = 0, X = 0;
+        if (uni) {
+            W = (d[0] + d[1]) + (d[2] + d[3]);
+            X = ((double)x0 * d[0] + (double)(x0 + 1) * d[1]) + ((double)(x0 + 2) * d[2] + (double)(x0 + 3) * d[3]);
+        } else {   // sub-runs of a thread that straddles a boundary go out directly
+            int cur = lab[0];
+            double w = d[0], x = (double)x0 * d[0];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                if (lab[k] == cur) { w += d[k]; x += (double)(x0 + k) * d[k]; }
+                else { cen_emit(cur, w, x, Y, hash, acc, Kcap, touch); cur = lab[k]; w = d[k]; x = (double)(x0 + k) * d[k]; }
+            }
+            cen_emit(cur, w, x, Y, hash, acc, Kcap, touch);
+        }
+        // segmented reduction over the uniform threads; a non-uniform thread is a segment of its own (bit 31 is free:
+        // real labels have y < 32768) that contributes nothing
+        const unsigned key = uni ? (unsigned)lab[0] : (0xC0000000u | (unsigned)lane);
+        const unsigned left = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = lane == 0 || key != left;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const unsigned after = (heads >> 1) >> lane;   // bit k: lane + 1 + k starts a new segment
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {             // lane + o lies in this lane's segment iff no head in (lane, lane + o]
+            const double W2 = __shfl_down_sync(0xffffffffu, W, o), X2 = __shfl_down_sync(0xffffffffu, X, o);
+            if (lane + o < 32 && (after & ((1u << o) - 1u)) == 0) { W += W2; X += X2; }
+        }
+        if (head && uni) cen_emit(lab[0], W, X, Y, hash, acc, Kcap, touch);
+    }
+    if (want_energy) {
+        e_loc = warp_sum(e_loc);
+        if (lane == 0 && e_loc != 0.0) atomicAdd(acc + 4 * (size_t)Kcap, e_loc);
+    }
+}
+
+// labels: dense packed labels of the context's rows (device, nrows * n int32, 16-byte aligned); density: the same rows.
+cudaError_t srm_launch_centroid_dense(cudaStream_t st, const int *labels, const float *density, SrmHash hash, SrmGrid g,
+                                      double *acc, int Kcap, int want_energy, int touch) {
+    const size_t groups = (size_t)g.nrows() * (size_t)(g.n >> 2);
+    size_t blocks = (groups + CEN_NT - 1) / CEN_NT;
+    const size_t resident = (size_t)148 * CEN_MINCTA * 4;   // a few waves: every thread streams several groups
+    if (blocks > resident) blocks = resident;
+    SRM_COUNT(), k_centroid_dense<<<(unsigned)blocks, CEN_NT, 0, st>>>(reinterpret_cast<const int4 *>(labels),
+                                                                       reinterpret_cast<const float4 *>(density), hash, g.n, g.row0,
+                                                                       g.nrows(), acc, Kcap, want_energy, touch);
+    return cudaGetLastError();
+}

@@ -246,6 +246,9 @@ void srm_launch_update(cudaStream_t st, const int *sites_in, int *sites_out, dou
 void srm_launch_nonzero_bits_f32(cudaStream_t st, const float *v, size_t count, uint32_t *out);
 void srm_launch_nonzero_bits_u8(cudaStream_t st, const unsigned char *v, size_t count, uint32_t *out);
 void srm_launch_signal(cudaStream_t st, SrmCtl *ctl, SrmPeers peers, int respect_stop);
+// stand-alone centroid pass over a dense label map (srm_centroid.cu): labels / density = the context's rows
+cudaError_t srm_launch_centroid_dense(cudaStream_t st, const int *labels, const float *density, SrmHash hash, SrmGrid g,
+                                      double *acc, int Kcap, int want_energy, int touch);
 void srm_preload_kernels();   // resolves every kernel of the loop up front (lazy module loading may otherwise synchronise
                               // the device in the middle of a launch sequence, while a kernel spins on a peer's flag)
 void srm_launch_sites_from_map(cudaStream_t st, const int *site_map, size_t N, int *sites_out, int *blockcnt,

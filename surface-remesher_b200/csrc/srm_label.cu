@@ -554,9 +554,9 @@ __global__ void __launch_bounds__(EXP_NT) k_expand2(SrmRle R, int n, int *__rest
 }
 
 #ifndef SRM_EXPAND_DEFAULT
-#define SRM_EXPAND_DEFAULT 0
+#define SRM_EXPAND_DEFAULT 1   // measured on the B200 (profiles/r2_stream_kernels.json): 73.9 us against 100.0 us at 8192^2
 #endif
-// 1 = two-level k_expand2, 0 = k_expand (A/B baseline).  SRM_EXPAND_V in the environment (read once) or
+// 1 = two-level k_expand2 (default), 0 = k_expand (the A/B baseline, kept for tests/test_gpu_variants.py).  SRM_EXPAND_V in the environment (read once) or
 // srm_set_variant("expand", v) (measurement tools) override the compiled default.
 int g_srm_expand_v = -1;
 static int expand_variant() {

@@ -15,7 +15,7 @@
 #include <stdlib.h>
 
 #ifndef SRM_PREFIX_DEFAULT
-#define SRM_PREFIX_DEFAULT 0
+#define SRM_PREFIX_DEFAULT 1   // measured on the B200 (profiles/r2_stream_kernels.json): 0.319 ms against 0.572 ms at 8192^2
 #endif
 
 // ------------------------------------------------------------------ prefix sums (once per call)
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(PFX_NT) k_prefix(const float *__restrict__ den
     }
 }
 
-// 1 = 256-bit stores, 0 = 128/64-bit stores (the round-1 form; A/B baseline).  SRM_PREFIX_V in the environment (read
+// 1 = 256-bit stores (default), 0 = 128/64-bit stores (the round-1 form; A/B baseline, kept for tests/test_gpu_variants.py).  SRM_PREFIX_V in the environment (read
 // once) or srm_set_variant("prefix", v) (measurement tools) override the compiled default.
 int g_srm_prefix_v = -1;
 static int prefix_variant() {

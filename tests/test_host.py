@@ -175,3 +175,41 @@ def test_examples_run_on_the_gpu(tmp_path):
     """The same two programs on a GPU box: the C-ABI example and the drop-in caller complete a Lloyd run."""
     test_header_is_plain_c_and_example_links(tmp_path)
     test_dropin_caller_links_and_fails_like_gpuErrchk(tmp_path)
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_host_scans_match_numpy(threads):
+    """srm_host.cu: the block-wise scans of the seed map (128-bit OR reduction, pixel loop only in blocks that hold a site)
+    and of the constraint mask against a numpy restatement: sizes that leave ragged tails per thread, a 2-byte aligned
+    base pointer, sites at block borders and in the x = 0 / y = 0 corner (packed value 0), dense stretches."""
+    import surface_remesher_b200 as S
+    L = S.api.lib()
+    rng = np.random.default_rng(7 + threads)
+    assert L.srm_host_config(threads, 0) == 0
+    try:
+        for pixels in (1, 31, 64, 65, 1000, 4099, 256 * 256 + 17):
+            raw = np.full(2 * pixels + 1, I.MARK, np.int16)
+            a = raw[1:]                                   # base pointer aligned to 2 bytes only
+            k = min(pixels, max(1, pixels // 50))
+            idx = np.unique(np.concatenate([rng.choice(pixels, size=k, replace=False), [0, pixels - 1, min(63, pixels - 1), min(64, pixels - 1)]]))
+            a[2 * idx] = rng.integers(0, 32767, size=len(idx)); a[2 * idx + 1] = rng.integers(0, 32767, size=len(idx))
+            a[0] = 0; a[1] = 0                            # site (0, 0): packed value 0 must be found
+            if pixels > 300:
+                a[2 * 100:2 * 228:2] = 5                  # 128 consecutive sites
+            exp = np.array([int(np.uint16(a[2 * i])) | (int(np.uint16(a[2 * i + 1])) << 16) for i in range(pixels) if a[2 * i] != I.MARK], np.int64)
+            out = np.empty(pixels + 1, np.int32); cnt = C.c_int()
+            assert L.srm_scan_site_map_host(a.ctypes.data_as(C.c_void_p), C.c_size_t(pixels), out.ctypes.data_as(C.c_void_p), pixels + 1, C.byref(cnt)) == 0
+            assert cnt.value == len(exp) and (out[: cnt.value].astype(np.int64) & 0xffffffff == exp).all()
+            # capacity smaller than the count: the count is still reported
+            assert L.srm_scan_site_map_host(a.ctypes.data_as(C.c_void_p), C.c_size_t(pixels), out.ctypes.data_as(C.c_void_p), 0, C.byref(cnt)) == 0
+            assert cnt.value == len(exp)
+        for n, r0, r1 in ((256, 0, 256), (512, 64, 448), (264, 3, 200)):
+            m = np.zeros((n, n), np.uint8)
+            ys = rng.integers(0, n, 300); xs = rng.integers(0, n, 300)
+            m[ys, xs] = rng.integers(1, 255, 300)
+            m[r0, :] = 1; m[r1 - 1, n - 1] = 255; m[r0, 0] = 7
+            got = np.sort(S.api.scan_mask(m, n, r0, r1))
+            yy, xx = np.nonzero(m[r0:r1])
+            assert (got == np.sort((xx | ((yy + r0) << 16)).astype(np.int32))).all()
+    finally:
+        L.srm_host_config(0, 0)

@@ -2,7 +2,8 @@
 """The two streaming kernels of a gCVT call on the headline grid, both builds of each (srm_set_variant):
 k_prefix (4 B/px read, 24 B/px written; 0 = 128/64-bit stores, 1 = 256-bit stores) and k_expand (4 B/px written from
 ~20 MB of runs; 0 = binary search per 4-pixel group, 1 = two-level lookup), device time per launch from CUDA events
-(srm_time_kernel: 20 launches after one untimed), as GB/s against the measured copy and write-only stream rates.
+(srm_time_kernel: 20 launches after one untimed), as GB/s against the measured copy and write-only stream rates; and the
+stand-alone centroid pass over the dense label map (k_centroid_dense, 8 B/px read).
 
     python tools/bench_streams.py [--n 8192] [--sites 100000] > gpurun_out/streams.json
 """
@@ -45,6 +46,13 @@ def main():
                 "k_expand_ms": te, "k_expand_GBs": (4.0 * N + 8.0 * runs) / te / 1e6,
                 "k_expand_frac_of_copy_peak": (4.0 * N + 8.0 * runs) / te / 1e6 / peak}
         S.api.set_variant("prefix", -1); S.api.set_variant("expand", -1)
+        # the stand-alone centroid pass over the dense label map (srm_centroid.cu): 8 B/px read + one hash bucket and three
+        # fp64 REDs per run; next to it the run-based accumulation kernel it is the alternative to (per run: 16 B prefix pair)
+        tc = min(c.time_kernel("centroid", 20) for _ in range(3))
+        tce = min(c.time_kernel("centroid_energy", 20) for _ in range(3))
+        out["centroid_dense"] = {"ms": tc, "GBs": 8.0 * N / tc / 1e6, "frac_of_copy_peak": 8.0 * N / tc / 1e6 / peak,
+                                 "with_energy_ms": tce, "with_energy_frac_of_copy_peak": 8.0 * N / tce / 1e6 / peak,
+                                 "algorithmic_bytes": 8.0 * N}
     print(json.dumps(out), flush=True)
 
 

@@ -10,7 +10,7 @@ CS=surface-remesher_b200/csrc
 make -C $CS -j4 >/dev/null
 mkdir -p build/variants/obj_$name
 objs=""
-for s in srm_api.cu srm_label.cu srm_band.cu srm_jfa.cu srm_lloyd.cu srm_raster.cu srm_recover.cu srm_host.cu; do
+for s in srm_api.cu srm_label.cu srm_band.cu srm_jfa.cu srm_centroid.cu srm_lloyd.cu srm_raster.cu srm_recover.cu srm_host.cu; do
   if [[ " $srcs " == *" $s "* ]]; then
     /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v $flags \
         -c $CS/$s -o build/variants/obj_$name/${s%.cu}.o 2> build/variants/obj_$name/${s%.cu}.ptxas.log
