@@ -13,20 +13,28 @@
 // cost at its roofline": 8 B/px * N streamed once.
 //
 // One warp = 128 consecutive pixels of one row (n is a multiple of 256, so a warp never straddles rows); a thread owns 4
-// pixels (one 128-bit load of labels, one of the density).  Threads whose 4 labels agree ("uniform", ~85 % at 26-pixel
-// runs) enter a segmented reduction over the warp: heads are the lanes whose label differs from their left neighbour's,
-// a lane adds its partner at distance o only if no head lies in between (read off the ballot of the heads), so
-// non-adjacent runs of one label (possible in approximate labellings) are never merged across the lanes between them,
-// and five shuffle steps leave every segment's (W, X) in its head lane.  Heads look the site id up in the pixel -> id hash and issue three fp64 REDs
-// (W, X, Y * W).  Threads that straddle a run boundary add their sub-runs directly.  North_star's "shared-memory
-// per-site accumulators": a shared-memory fp64 atomicAdd is a CAS loop (ATOMS.CAST.SPIN, ~64 cycles per warp
-// instruction), dearer than the global RED it would save (1.3 cycles per lane; profiles/r2_kernel_log.md), so the
-// per-warp segment sums go to global memory directly — one RED set per run and row, exactly what the band kernel issues.
+// pixels (one 128-bit streaming load of labels, one of the density; the loads of the next step are issued before the
+// current one is reduced).  Every thread ends up with ONE item (label, W, X) for the warp's segmented reduction:
+//   * a thread whose 4 labels agree ("uniform", ~85 % at 26-pixel runs): its label and sums;
+//   * a thread that straddles run boundaries: its TRAILING sub-run (the run that continues into the next lane); its
+//     LEADING sub-run is handed to the lane on its left (one shuffle step) when that lane's item carries the same label
+//     — i.e. it is the tail of the run the left lanes are summing — and complete runs inside the thread (<= 3 pixels,
+//     rare) go out directly.
+// Heads are the lanes that start a run: lane 0, every straddling lane (its item starts inside the lane), and uniform
+// lanes whose label differs from the item on their left.  A lane adds its partner at distance o only if no head lies
+// in between (read off the ballot of the heads), so non-adjacent runs of one label (possible in approximate labellings)
+// are never merged, and five shuffle steps leave every run's (W, X) in its head lane.  Heads look the site id up in the
+// pixel -> id hash and issue three fp64 REDs (W, X, Y * W): one set per run and row (+ one per run that crosses a
+// 128-pixel warp boundary), what the band kernel issues from its run lists.  North_star's "shared-memory per-site
+// accumulators": a shared-memory fp64 atomicAdd is a CAS loop (ATOMS.CAST.SPIN, ~64 cycles per warp instruction),
+// dearer than the global RED it would save (1.3 cycles per lane; profiles/r2_kernel_log.md), so the per-warp run sums go
+// to global memory directly.
 //
 // Sums are fp64 in tree order; the float the update law rounds them to is what the parity tests compare
-// (tests/test_gpu_centroid.py: per-site sums against the run-based kernel and the oracle's direct sums, the updated
-// sites bit-exact against the oracle's step).
+// (tests/test_gpu_centroid.py: per-site sums against the run-based kernel and direct numpy sums, the updated sites
+// bit-exact against the oracle's step).
 #include "srm_common.cuh"
+#include <stdlib.h>
 
 #define CEN_NT 256
 #define CEN_MINCTA 6
@@ -51,9 +59,15 @@ k_centroid_dense(const int4 *__restrict__ labels4, const float4 *__restrict__ de
     const unsigned groups = (unsigned)nrows * gpr;                       // <= 32768 * 8192 = 2^28
     const unsigned stride = gridDim.x * CEN_NT;
     double e_loc = 0;
-    for (unsigned g = blockIdx.x * CEN_NT + threadIdx.x; g < groups; g += stride) {   // warp-uniform trip count
-        const int4 L = labels4[g];
-        const float4 D = dens4[g];
+    unsigned g = blockIdx.x * CEN_NT + threadIdx.x;                      // warp-uniform trip count: groups % 32 == 0
+    int4 L = make_int4(0, 0, 0, 0);
+    float4 D = make_float4(0, 0, 0, 0);
+    if (g < groups) { L = __ldcs(labels4 + g); D = __ldcs(dens4 + g); }
+    while (g < groups) {
+        const unsigned gn = g + stride;
+        int4 Ln = L;
+        float4 Dn = D;
+        if (gn < groups) { Ln = __ldcs(labels4 + gn); Dn = __ldcs(dens4 + gn); }   // in flight while this step is reduced
         const unsigned r = g / gpr;
         const int x0 = (int)(g - r * gpr) << 2, Y = row0 + (int)r;
         const int lab[4] = {L.x, L.y, L.z, L.w};
@@ -66,33 +80,45 @@ k_centroid_dense(const int4 *__restrict__ labels4, const float4 *__restrict__ de
             }
         }
         const bool uni = lab[0] == lab[1] && lab[1] == lab[2] && lab[2] == lab[3];
-        double W = 0, X = 0;
+        // item: the sub-run that reaches the thread's last pixel; WL / XL: the leading sub-run of a straddling thread
+        int item = lab[3];
+        double W, X, WL = 0, XL = 0;
         if (uni) {
             W = (d[0] + d[1]) + (d[2] + d[3]);
             X = ((double)x0 * d[0] + (double)(x0 + 1) * d[1]) + ((double)(x0 + 2) * d[2] + (double)(x0 + 3) * d[3]);
-        } else {   // sub-runs of a thread that straddles a boundary go out directly
+        } else {
             int cur = lab[0];
             double w = d[0], x = (double)x0 * d[0];
+            bool leading = true;
 #pragma unroll
             for (int k = 1; k < 4; ++k) {
                 if (lab[k] == cur) { w += d[k]; x += (double)(x0 + k) * d[k]; }
-                else { cen_emit(cur, w, x, Y, hash, acc, Kcap, touch); cur = lab[k]; w = d[k]; x = (double)(x0 + k) * d[k]; }
+                else {
+                    if (leading) { WL = w; XL = x; leading = false; }
+                    else cen_emit(cur, w, x, Y, hash, acc, Kcap, touch);   // a complete run inside the thread
+                    cur = lab[k]; w = d[k]; x = (double)(x0 + k) * d[k];
+                }
             }
-            cen_emit(cur, w, x, Y, hash, acc, Kcap, touch);
+            W = w; X = x;
         }
-        // segmented reduction over the uniform threads; a non-uniform thread is a segment of its own (bit 31 is free:
-        // real labels have y < 32768) that contributes nothing
-        const unsigned key = uni ? (unsigned)lab[0] : (0xC0000000u | (unsigned)lane);
-        const unsigned left = __shfl_up_sync(0xffffffffu, key, 1);
-        const bool head = lane == 0 || key != left;
+        // hand the leading sub-run to the left lane if that lane's item is the same run (same label, adjacent pixels)
+        const int left = __shfl_up_sync(0xffffffffu, item, 1);
+        const bool accepted = !uni && lane > 0 && left == lab[0];
+        if (!uni && !accepted) cen_emit(lab[0], WL, XL, Y, hash, acc, Kcap, touch);   // run ends here and starts at or before the thread's first pixel
+        {
+            const double gW = __shfl_down_sync(0xffffffffu, accepted ? WL : 0.0, 1), gX = __shfl_down_sync(0xffffffffu, accepted ? XL : 0.0, 1);
+            if (lane < 31) { W += gW; X += gX; }
+        }
+        const bool head = lane == 0 || !uni || item != left;
         const unsigned heads = __ballot_sync(0xffffffffu, head);
-        const unsigned after = (heads >> 1) >> lane;   // bit k: lane + 1 + k starts a new segment
+        const unsigned after = (heads >> 1) >> lane;   // bit k: lane + 1 + k starts a new run
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {             // lane + o lies in this lane's segment iff no head in (lane, lane + o]
+        for (int o = 1; o < 32; o <<= 1) {             // lane + o lies in this lane's run iff no head in (lane, lane + o]
             const double W2 = __shfl_down_sync(0xffffffffu, W, o), X2 = __shfl_down_sync(0xffffffffu, X, o);
             if (lane + o < 32 && (after & ((1u << o) - 1u)) == 0) { W += W2; X += X2; }
         }
-        if (head && uni) cen_emit(lab[0], W, X, Y, hash, acc, Kcap, touch);
+        if (head) cen_emit(item, W, X, Y, hash, acc, Kcap, touch);
+        L = Ln; D = Dn; g = gn;
     }
     if (want_energy) {
         e_loc = warp_sum(e_loc);
@@ -105,7 +131,9 @@ cudaError_t srm_launch_centroid_dense(cudaStream_t st, const int *labels, const 
                                       double *acc, int Kcap, int want_energy, int touch) {
     const size_t groups = (size_t)g.nrows() * (size_t)(g.n >> 2);
     size_t blocks = (groups + CEN_NT - 1) / CEN_NT;
-    const size_t resident = (size_t)148 * CEN_MINCTA * 4;   // a few waves: every thread streams several groups
+    // persistent: one wave of resident CTAs, every thread streams its share (SRM_CEN_WAVES, read once: measurement knob)
+    static const int waves = []() { const char *e = getenv("SRM_CEN_WAVES"); const int v = e ? atoi(e) : 1; return v >= 1 && v <= 64 ? v : 1; }();
+    const size_t resident = (size_t)148 * CEN_MINCTA * (size_t)waves;
     if (blocks > resident) blocks = resident;
     SRM_COUNT(), k_centroid_dense<<<(unsigned)blocks, CEN_NT, 0, st>>>(reinterpret_cast<const int4 *>(labels),
                                                                        reinterpret_cast<const float4 *>(density), hash, g.n, g.row0,

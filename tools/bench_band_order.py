@@ -25,16 +25,18 @@ def main():
     ap.add_argument("--n", type=int, default=8192)
     ap.add_argument("--sites", type=int, default=100000)
     ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--orders", default="0,1,0,1", help="settings to run, in order (e.g. \"0\" for one timing of the row order, "
+                    "used with SRM_BAND_RPW=2 in the environment for the 16-row band A/B)")
     a = ap.parse_args()
     import torch
     n = a.n
     dens, mask, vor = bench.make_inputs(n, a.sites, pinned=False)
-    out = {"grid": n, "sites": a.sites, "steps": a.steps, "runs": []}
+    out = {"grid": n, "sites": a.sites, "steps": a.steps, "SRM_BAND_RPW": os.environ.get("SRM_BAND_RPW", "1"), "runs": []}
     ref = None
     with S.Context(n) as c:
         c.set_stream(torch.cuda.current_stream().cuda_stream)
         c.set_density(dens); c.set_mask(mask)
-        for order in (0, 1, 0, 1):
+        for order in [int(x) for x in a.orders.split(",")]:
             c.set_option("band_order", order)
             c.set_site_map(vor)
             c.iterate(12)
@@ -52,7 +54,7 @@ def main():
             r = {"band_order": order, "k_band_us": round(st["band_fused"] / a.steps * 1e3, 2),
                  "profiled_step_us": round(st["iteration"] / a.steps * 1e3, 2), "plain_step_us": round(ms / a.steps * 1e3, 2),
                  "it_per_s": round(a.steps / ms * 1e3, 1), "sites_identical": bool(np.array_equal(sites, ref)),
-                 "perm_is_identity": bool((perm == np.arange(len(perm))).all()),
+                 "sites_sha1": bench.sites_sha1(sites), "perm_is_identity": bool((perm == np.arange(len(perm))).all()),
                  "cost_min_mean_max": [int(cost.min()), int(cost.mean()), int(cost.max())]}
             out["runs"].append(r)
             print(json.dumps(r), file=sys.stderr, flush=True)
