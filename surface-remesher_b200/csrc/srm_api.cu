@@ -818,11 +818,12 @@ extern "C" int srm_host_config(int threads, int chunk_kb) {
 // Process-wide choice between two builds of a streaming kernel (measurement tools and A/B tests): which = "expand"
 // (runs -> dense labels: 0 one binary search per 4-pixel group, 1 two-level lookup) or "prefix" (fp64 prefix sums:
 // 0 128/64-bit stores, 1 256-bit stores); value < 0 = back to the environment / compiled default.
-extern int g_srm_expand_v, g_srm_prefix_v;
+extern int g_srm_expand_v, g_srm_prefix_v, g_srm_centroid_v;
 extern "C" int srm_set_variant(const char *which, int value) {
     if (!which) return fail(SRM_ERR_ARG, "srm_set_variant: null argument");
     if (!strcmp(which, "expand")) { g_srm_expand_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
     if (!strcmp(which, "prefix")) { g_srm_prefix_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
+    if (!strcmp(which, "centroid")) { g_srm_centroid_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
     return fail(SRM_ERR_ARG, "srm_set_variant: unknown kernel %s", which);
 }
 

@@ -11,6 +11,15 @@ import _oracle as O
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["v0", "v1"], autouse=True)
+def variant(request):
+    """Both builds of the kernel (srm_centroid.cu: 0 = k_centroid_dense, 1 = k_centroid_dense2, fewer instructions)."""
+    import surface_remesher_b200 as S
+    S.api.set_variant("centroid", request.param)
+    yield request.param
+    S.api.set_variant("centroid", -1)
+
+
 def _case(kind, n, k):
     dens = I.density_uniform(n) if kind == "uniform" else I.density_c3(n)
     mask = None if kind == "uniform" else I.mask_c3(dens)

@@ -48,11 +48,14 @@ def main():
         S.api.set_variant("prefix", -1); S.api.set_variant("expand", -1)
         # the stand-alone centroid pass over the dense label map (srm_centroid.cu): 8 B/px read + one hash bucket and three
         # fp64 REDs per run; next to it the run-based accumulation kernel it is the alternative to (per run: 16 B prefix pair)
-        tc = min(c.time_kernel("centroid", 20) for _ in range(3))
-        tce = min(c.time_kernel("centroid_energy", 20) for _ in range(3))
-        out["centroid_dense"] = {"ms": tc, "GBs": 8.0 * N / tc / 1e6, "frac_of_copy_peak": 8.0 * N / tc / 1e6 / peak,
-                                 "with_energy_ms": tce, "with_energy_frac_of_copy_peak": 8.0 * N / tce / 1e6 / peak,
-                                 "algorithmic_bytes": 8.0 * N}
+        for v in (0, 1):   # 0 = k_centroid_dense (first build), 1 = k_centroid_dense2 (default)
+            S.api.set_variant("centroid", v)
+            tc = min(c.time_kernel("centroid", 20) for _ in range(3))
+            tce = min(c.time_kernel("centroid_energy", 20) for _ in range(3))
+            out[f"centroid_dense_v{v}"] = {"ms": tc, "GBs": 8.0 * N / tc / 1e6, "frac_of_copy_peak": 8.0 * N / tc / 1e6 / peak,
+                                           "with_energy_ms": tce, "with_energy_frac_of_copy_peak": 8.0 * N / tce / 1e6 / peak,
+                                           "algorithmic_bytes": 8.0 * N, "SRM_CEN_WAVES": os.environ.get("SRM_CEN_WAVES", "4")}
+        S.api.set_variant("centroid", -1)
     print(json.dumps(out), flush=True)
 
 
