@@ -199,8 +199,8 @@ int srm_debug_band_order(srm_ctx *ctx, int *perm_out, int *cost_out, int capacit
 int srm_host_config(int threads, int chunk_kb);
 
 /* Measurement / A-B tests: process-wide choice between two builds of a streaming kernel.  which = "expand" (runs ->
- * dense labels), "prefix" (fp64 prefix sums) or "centroid" (srm_accumulate_dense); value 0 / 1, < 0 = environment
- * (SRM_EXPAND_V, SRM_PREFIX_V, SRM_CENTROID_V) / compiled default (1 for all three). */
+ * dense labels; 0 / 1 / 2), "prefix" (fp64 prefix sums; 0 / 1) or "centroid" (srm_accumulate_dense; 0 / 1); < 0 =
+ * environment (SRM_EXPAND_V, SRM_PREFIX_V, SRM_CENTROID_V) / compiled default (the highest number of each). */
 int srm_set_variant(const char *which, int value);
 
 /* Measurement: device milliseconds per launch of a streaming kernel on the context's resident data (`reps` launches

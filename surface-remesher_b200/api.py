@@ -550,8 +550,8 @@ def host_config(threads=0, chunk_kb=0):
 
 
 def set_variant(which, value):
-    """Measurement / A-B tests: process-wide choice between two builds of a streaming kernel ("expand", "prefix",
-    "centroid"); -1 = back to the compiled default."""
+    """Measurement / A-B tests: process-wide choice between the builds of a streaming kernel ("expand": 0 / 1 / 2,
+    "prefix": 0 / 1, "centroid": 0 / 1); -1 = back to the compiled default."""
     _ck(lib().srm_set_variant(which.encode(), int(value)))
 
 

@@ -821,7 +821,7 @@ extern "C" int srm_host_config(int threads, int chunk_kb) {
 extern int g_srm_expand_v, g_srm_prefix_v, g_srm_centroid_v;
 extern "C" int srm_set_variant(const char *which, int value) {
     if (!which) return fail(SRM_ERR_ARG, "srm_set_variant: null argument");
-    if (!strcmp(which, "expand")) { g_srm_expand_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
+    if (!strcmp(which, "expand")) { g_srm_expand_v = value < 0 ? -1 : (value > 2 ? 2 : value); return SRM_OK; }
     if (!strcmp(which, "prefix")) { g_srm_prefix_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
     if (!strcmp(which, "centroid")) { g_srm_centroid_v = value < 0 ? -1 : (value != 0); return SRM_OK; }
     return fail(SRM_ERR_ARG, "srm_set_variant: unknown kernel %s", which);

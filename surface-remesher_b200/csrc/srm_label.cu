@@ -553,19 +553,82 @@ __global__ void __launch_bounds__(EXP_NT) k_expand2(SrmRle R, int n, int *__rest
     }
 }
 
+// Bitmap form: the run starts of the row become a 1 bit/px bitmap in shared memory with an exclusive popcount prefix per
+// 32-pixel word, so the run of pixel x is a prefix popcount — two shared-memory words, one POPC — and the runs of the three
+// following pixels are that plus their own start bits: no search and no data-dependent loop.  k_expand2 is bound by
+// instruction issue (ncu, profiles/r2_ncu_streams_s14.md: 65.7 M warp instructions = 125 per 4-pixel group of a warp,
+// issue slots 82 % busy, 3.6 TB/s of stores); this form needs ~30 per group.  Run lists longer than the staging area
+// are read from global memory by the same code.
+__global__ void __launch_bounds__(EXP_NT) k_expand3(SrmRle R, int n, int *__restrict__ labels) {
+    __shared__ __align__(16) int2 s_runs3[EXP2_CAP];
+    __shared__ unsigned s_bits[1024];   // n / 32 <= 1024 words: bit x set iff a run starts at pixel x
+    __shared__ int s_pre[1024];         // run starts in the words before this one
+    __shared__ int s_wsum[EXP_NT / 32];
+    __shared__ __align__(8) unsigned long long bar;
+    const int r = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (R.off[r] < 0) return;   // the pool was exhausted: the host repeats the labelling with a larger one
+    const int cnt = R.cnt[r];
+    const int2 *runs = R.pool + R.off[r];
+    int4 *out = reinterpret_cast<int4 *>(labels + (size_t)r * n);
+    if (cnt == 0) {   // no site at all
+        for (int q = t; q < (n >> 2); q += EXP_NT) out[q] = make_int4(SRM_SENT, SRM_SENT, SRM_SENT, SRM_SENT);
+        return;
+    }
+    const bool staged = cnt <= EXP2_CAP;
+    if (staged && t == 0) mbar_init(&bar, 1);
+    for (int w = t; w < 1024; w += EXP_NT) s_bits[w] = 0u;
+    __syncthreads();
+    if (staged) {
+        if (t == 0) bulk_load(s_runs3, runs, (unsigned)(((cnt + 1) & ~1) * sizeof(int2)), &bar);
+        mbar_wait(&bar, 0);
+        runs = s_runs3;
+    }
+    for (int e = t; e < cnt; e += EXP_NT) {   // starts are distinct and increasing; run 0 starts at pixel 0
+        const int x = runs[e].y;
+        atomicOr(&s_bits[x >> 5], 1u << (x & 31));
+    }
+    __syncthreads();
+    {   // exclusive prefix of the popcounts over the 1024 words: 4 consecutive words per thread, warp scan, 8 warp totals
+        const int c0 = __popc(s_bits[4 * t]), c1 = __popc(s_bits[4 * t + 1]), c2 = __popc(s_bits[4 * t + 2]), c3 = __popc(s_bits[4 * t + 3]);
+        const int tot = c0 + c1 + c2 + c3;
+        const int incl = warp_incl_scan(tot, lane);
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        int base = incl - tot;
+#pragma unroll
+        for (int k = 0; k < EXP_NT / 32; ++k) base += (k < wid) ? s_wsum[k] : 0;
+        s_pre[4 * t] = base; s_pre[4 * t + 1] = base + c0; s_pre[4 * t + 2] = base + c0 + c1; s_pre[4 * t + 3] = base + c0 + c1 + c2;
+    }
+    __syncthreads();
+    for (int q = t; q < (n >> 2); q += EXP_NT) {
+        const int x = q << 2, w = x >> 5, b = x & 31;   // b is a multiple of 4: b + 3 <= 31
+        const unsigned word = s_bits[w];
+        const int e0 = max(s_pre[w] + __popc(word & ((2u << b) - 1u)) - 1, 0);   // run starts at pixels <= x, minus one
+        const int e1 = e0 + (int)((word >> (b + 1)) & 1u), e2 = e1 + (int)((word >> (b + 2)) & 1u), e3 = e2 + (int)((word >> (b + 3)) & 1u);
+        int4 v;
+        v.x = runs[e0].x;
+        v.y = runs[e1].x;
+        v.z = runs[e2].x;
+        v.w = runs[e3].x;
+        out[q] = v;
+    }
+}
+
 #ifndef SRM_EXPAND_DEFAULT
-#define SRM_EXPAND_DEFAULT 1   // measured on the B200 (profiles/r2_stream_kernels.json): 73.9 us against 100.0 us at 8192^2
+#define SRM_EXPAND_DEFAULT 2   // measured on the B200 (profiles/r2_stream_kernels*.json): 1: 73.9 us against 0: 100.0 us at 8192^2
 #endif
-// 1 = two-level k_expand2 (default), 0 = k_expand (the A/B baseline, kept for tests/test_gpu_variants.py).  SRM_EXPAND_V in the environment (read once) or
+// 2 = bitmap form k_expand3 (default), 1 = two-level k_expand2, 0 = k_expand (all three run in tests/test_gpu_variants.py).  SRM_EXPAND_V in the environment (read once) or
 // srm_set_variant("expand", v) (measurement tools) override the compiled default.
 int g_srm_expand_v = -1;
 static int expand_variant() {
-    if (g_srm_expand_v < 0) { const char *e = getenv("SRM_EXPAND_V"); g_srm_expand_v = e ? atoi(e) != 0 : SRM_EXPAND_DEFAULT; }
+    if (g_srm_expand_v < 0) { const char *e = getenv("SRM_EXPAND_V"); const int v = e ? atoi(e) : SRM_EXPAND_DEFAULT; g_srm_expand_v = v < 0 || v > 2 ? SRM_EXPAND_DEFAULT : v; }
     return g_srm_expand_v;
 }
 
 cudaError_t srm_launch_expand(cudaStream_t st, SrmRle rle, SrmGrid g, int *labels) {
-    if (expand_variant()) SRM_COUNT(), k_expand2<<<g.nrows(), EXP_NT, 0, st>>>(rle, g.n, labels);
+    const int ev = expand_variant();
+    if (ev == 2) SRM_COUNT(), k_expand3<<<g.nrows(), EXP_NT, 0, st>>>(rle, g.n, labels);
+    else if (ev == 1) SRM_COUNT(), k_expand2<<<g.nrows(), EXP_NT, 0, st>>>(rle, g.n, labels);
     else SRM_COUNT(), k_expand<<<g.nrows(), EXP_NT, EXP_CAP * sizeof(int2), st>>>(rle, g.n, labels);
     return cudaGetLastError();
 }

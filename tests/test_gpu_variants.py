@@ -1,5 +1,6 @@
-"""The two builds of each streaming kernel must give identical results (and the oracle's):
-  "expand"  runs -> dense labels: 0 = one binary search per 4-pixel group (k_expand), 1 = two-level lookup (k_expand2)
+"""The builds of each streaming kernel must give identical results (and the oracle's):
+  "expand"  runs -> dense labels: 0 = one binary search per 4-pixel group (k_expand), 1 = two-level lookup (k_expand2),
+                                  2 = run-start bitmap + popcount prefix (k_expand3)
   "prefix"  fp64 prefix sums:     0 = 128/64-bit stores, 1 = 256-bit stores (STG.E.ENL2.256)
 Whichever is the compiled default, both are exercised here; the rest of the suite runs on the default."""
 import numpy as np
@@ -11,11 +12,11 @@ import _oracle as O
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1], ids=["v0", "v1"])
+@pytest.fixture(params=[0, 1, 2], ids=["v0", "v1", "v2"])
 def variant(request):
     import surface_remesher_b200 as S
     S.api.set_variant("expand", request.param)
-    S.api.set_variant("prefix", request.param)
+    S.api.set_variant("prefix", min(request.param, 1))
     yield request.param
     S.api.set_variant("expand", -1)
     S.api.set_variant("prefix", -1)

@@ -37,8 +37,8 @@ def main():
         c.label()
         runs, _ = c.debug_counts()
         out["runs"] = int(runs)
-        for v in (0, 1):
-            S.api.set_variant("prefix", v); S.api.set_variant("expand", v)
+        for v in (0, 1, 2):   # expand: 0 / 1 / 2 (bitmap form, default); prefix: 0 / 1 (default)
+            S.api.set_variant("prefix", min(v, 1)); S.api.set_variant("expand", v)
             tp = min(c.time_kernel("prefix", 20) for _ in range(3))
             te = min(c.time_kernel("expand", 20) for _ in range(3))
             out[f"variant{v}"] = {
