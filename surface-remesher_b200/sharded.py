@@ -113,8 +113,10 @@ class CudaBandEngine:
     def sites(self):
         return self.ctx.get_sites()
 
-    def labels(self):
-        return self.ctx.get_labels()
+    def labels(self, out=None):
+        """Dense labels of this band; `out`: a host array to fill instead of a fresh one (a fresh 134 MB numpy array costs
+        ~10 ms of first-touch page faults per call at 8192^2 on two ranks — callers that repeat the call reuse theirs)."""
+        return self.ctx.get_labels(out)
 
     def state(self):
         return self.ctx.state()
@@ -201,7 +203,7 @@ class ShardedLloyd:
         for _ in range(iters):
             self.step()
 
-    def final_labels(self):
-        """Labels of this band for the current sites (gcvt.cu:1149)."""
+    def final_labels(self, out=None):
+        """Labels of this band for the current sites (gcvt.cu:1149); `out`: host array [rows, n, 2] int16 to fill."""
         self.engine.label()
-        return self.engine.labels()
+        return self.engine.labels() if out is None else self.engine.labels(out)
