@@ -50,17 +50,33 @@ class CudaBandEngine:
         the ranks (one broadcast per band over NCCL/NVLink: n*n/8 bytes in total)."""
         n = self.ctx.n
         r0, r1 = bands[rank]
-        self.ctx.set_density_band(density[r0:r1])
-        ptr, words = self.ctx.shared_bits(0)
-        self._nzkeep = _CudaArray(ptr, words, "<i4")
-        nz = self.torch.as_tensor(self._nzkeep, device=self.device)
-        self.torch.cuda.current_stream(self.device).synchronize()
-        for q, (a, b) in enumerate(bands):
-            dist.broadcast(nz[a * n // 32: b * n // 32], src=q)
-        # the two sparse inputs: every rank scans ITS rows on the host; the lists of all ranks, concatenated in rank
-        # order, are the row-major scan of the whole arrays (the order a single GPU sees, so the site ids agree)
-        sites = scan_site_map(np.asarray(site_map).reshape(n, n, 2)[r0:r1])      # multi-threaded C scans (srm_host.cu)
-        mpx = scan_mask(mask, n, r0, r1) if mask is not None else np.zeros(0, np.int32)
+        # the two sparse inputs: every rank scans ITS rows on the host (multi-threaded C scans, srm_host.cu) while its rows
+        # of the density go up (both calls release the GIL); the lists of all ranks, concatenated in rank order, are the
+        # row-major scan of the whole arrays (the order a single GPU sees, so the site ids agree)
+        import threading
+        scanned = {}
+
+        def scan():
+            try:
+                scanned["sites"] = scan_site_map(np.asarray(site_map).reshape(n, n, 2)[r0:r1])
+                scanned["mpx"] = scan_mask(mask, n, r0, r1) if mask is not None else np.zeros(0, np.int32)
+            except BaseException as e:   # re-raised on the calling thread below
+                scanned["error"] = e
+        th = threading.Thread(target=scan)
+        th.start()
+        try:
+            self.ctx.set_density_band(density[r0:r1])
+            ptr, words = self.ctx.shared_bits(0)
+            self._nzkeep = _CudaArray(ptr, words, "<i4")
+            nz = self.torch.as_tensor(self._nzkeep, device=self.device)
+            self.torch.cuda.current_stream(self.device).synchronize()
+            for q, (a, b) in enumerate(bands):
+                dist.broadcast(nz[a * n // 32: b * n // 32], src=q)
+        finally:
+            th.join()
+        if "error" in scanned:
+            raise scanned["error"]
+        sites, mpx = scanned["sites"], scanned["mpx"]
         sites, mpx = self._allgather_lists(dist, [sites, mpx], len(bands))
         if mask is not None:
             self.ctx.set_mask_pixels(mpx)
